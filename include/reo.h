@@ -1,0 +1,143 @@
+/*
+ * reo.h -- C ABI of libreo_cuda.so: the B200-native REO core behind RankCompV3.jl's
+ *          `identify_degs` (reference: src/RankCompV3.jl:339-438, called from reoa() at
+ *          src/RankCompV3.jl:652-662).
+ *
+ * The reference has no FFI layer; the seam this library replaces is the Julia call
+ *     identify_degs(Matrix(df_expr), meta_group.Group, gene_names, pval_reo, pval_deg, padj_deg,
+ *                   ref_gene_vec, n_iter, n_conv)                       (src:652-662, sig. 339-350)
+ * INTEGRATION.md shows the `ccall` shim a maintainer would add.  Plain pointers and sizes only;
+ * no exceptions or aborts cross this boundary: every entry point returns a reo_status and
+ * leaves caller outputs untouched on failure.  A handle is re-entrant per handle, owns its CUDA
+ * streams, and never synchronises the legacy default stream.
+ *
+ * Conventions
+ *  - `data` is column-major r x c with leading dimension ld (Julia `Matrix`): data[i + ld*s]
+ *    is gene i in sample s.  Sample s belongs to level group_id[s] (0-based, levels numbered
+ *    in order of first appearance, i.e. Julia's `unique(group)`, src:353).
+ *  - K = 1 when gnum == 2 (src:387-389, 431-434), else gnum (one-vs-rest per level).
+ *  - `thresholds` is the 2 x gnum column-major Int32 matrix of src:362
+ *    (thresholds[0+2k] for level k, thresholds[1+2k] for the rest); NULL -> computed from pval_reo.
+ *  - Ties (|x-y| < 0.1, src:72) are broken by the deterministic coin documented in DESIGN.md
+ *    (`seed` of reo_create), which replaces the reference's rand(Bool) (src:73).
+ */
+#ifndef REO_H
+#define REO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REO_VERSION 100 /* 0.1.0 */
+
+typedef struct reo_handle_s* reo_handle_t;
+
+typedef enum {
+    REO_OK = 0,
+    REO_ERR_DIM = -1,         /* DimensionMismatch of src:355-356 (c != length(group), < 2 levels) */
+    REO_ERR_ARG = -2,         /* bad argument (NULL pointer, unknown dtype, negative size, ...)    */
+    REO_ERR_CUDA = -3,        /* CUDA runtime error, see reo_last_error                            */
+    REO_ERR_COMM = -4,        /* collective (NCCL / user all-gather callback) failed               */
+    REO_ERR_OOM = -5,         /* host or device allocation failed                                  */
+    REO_ERR_BOUNDS = -6,      /* r <= 10: the reference's BoundsError at src:411                   */
+    REO_ERR_UNSUPPORTED = -7, /* input outside what this build supports (see message)              */
+    REO_ERR_STATE = -8        /* stage-level call without a staged matrix                          */
+} reo_status;
+
+typedef enum { REO_I64 = 0, REO_F64 = 1, REO_I32 = 2, REO_F32 = 3 } reo_dtype;
+
+/* reo_create flags */
+#define REO_FLAG_NONE 0u
+/* reo_identify_degs / reo_stage flags */
+#define REO_DATA_ON_DEVICE 1u /* `data` is a device pointer on the handle's first device */
+
+#define REO_MAX_ITER_LOG 256
+
+/* Out-struct for logging: lets the Julia shim print the reference's @info lines (src:418-420). */
+typedef struct {
+    int32_t iters_done;                 /* evaluations performed for the last k                     */
+    int32_t converged;                  /* 1 if the n_conv criterion stopped the loop (src:419-422) */
+    int32_t n_deg[REO_MAX_ITER_LOG];    /* # DEGs per evaluation (src:418)                          */
+    int32_t n_ref[REO_MAX_ITER_LOG];    /* size of the reference set used by each evaluation        */
+    int32_t rank_bits;                  /* bit-planes per rank (B); planes staged = B + 1           */
+    int32_t sample_words;               /* 32-sample words staged (all levels, padded)              */
+    int64_t compares;                   /* ordered (gene, ref gene, sample) triples evaluated       */
+    double ms_stage;                    /* H2D + rank + bit-plane staging                           */
+    double ms_pairs;                    /* pair-count/class/table kernels (all iterations)          */
+    double ms_stats;                    /* McCullagh + empirical null + BH + mask kernels           */
+    double ms_total;                    /* whole call, device timeline                              */
+    int32_t pair_launches;              /* pair-kernel launches                                     */
+    int32_t kernel_launches;            /* all kernel launches of this call                         */
+} reo_stats;
+
+/* Multi-process sharding hook: all-gather `bytes_per_rank` bytes per rank, in place, inside the
+ * device buffer `dev_buf` (rank q's slice at offset q*bytes_per_rank).  The library has
+ * synchronised its stream before the call and expects the result to be complete on return.   */
+typedef int (*reo_allgather_fn)(void* ctx, void* dev_buf, uint64_t bytes_per_rank);
+
+int reo_version(void);
+
+/* ndev >= 1 devices driven by this (single) process; devs == NULL -> 0..ndev-1.
+ * seed keys the tie coins.  Replaces nothing in the reference (it has no handle). */
+int reo_create(reo_handle_t* out, int ndev, const int* devs, uint64_t seed, uint32_t flags);
+int reo_destroy(reo_handle_t h);
+const char* reo_last_error(reo_handle_t h); /* h may be NULL: last create error */
+
+/* One-process-per-GPU mode (torchrun): this handle is rank `rank` of `world`; gene-row tiles
+ * are sharded by rank and tables exchanged through `fn` (e.g. torch.distributed all_gather). */
+int reo_set_collective(reo_handle_t h, int rank, int world, reo_allgather_fn fn, void* ctx);
+
+/* get_major_reo_lower_count(sample_size, pval_threshold), src:81-92.  Host arithmetic. */
+int reo_threshold(int sample_size, double pval_reo);
+
+/*
+ * identify_degs, src:339-438: the whole path.  result: K x r x 15 doubles, k-major; per gene the
+ * 15 columns of src:398/405/665 (pval padj n11 n12 n13 n21 n22 n23 n31 n32 n33 d1 d2 se z1).
+ * updown: K x r (+1 "up", -1 "down", 0 "no change", src:426-429).  final_ref: K x r, the mask
+ * used by the last evaluation (may be NULL).  iters_done: K ints (may be NULL).  stats may be NULL.
+ */
+int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld,
+                      const int32_t* group_id, int32_t gnum, const int32_t* thresholds, double pval_reo,
+                      double pval_deg, double padj_deg, const uint8_t* ref_mask, int32_t n_iter, int32_t n_conv,
+                      uint32_t flags, double* result, int8_t* updown, uint8_t* final_ref, int32_t* iters_done,
+                      reo_stats* stats);
+
+/* ---- stage-level entry points (parity tests, benches, profilers) ------------------------- */
+
+/* K1: copy, dense-rank per sample, bit-slice, coin plane.  The staged matrix stays resident in
+ * the handle until the next reo_stage / reo_identify_degs / reo_destroy.  src:351-362 + 372. */
+int reo_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld,
+              const int32_t* group_id, int32_t gnum, uint32_t flags);
+int reo_stage_info(reo_handle_t h, int32_t* rank_bits, int32_t* sample_words, int32_t* gene_tiles);
+
+/* src:372-374 for a small block: for level k, nre[a*ncols+b] = # level-k samples where gene
+ * rows[a] "is greater" than gene cols[b], rest[...] likewise over all other samples.        */
+int reo_pair_counts(reo_handle_t h, int32_t k, const int32_t* rows, int32_t nrows, const int32_t* cols,
+                    int32_t ncols, int32_t* nre, int32_t* rest);
+
+/* src:366-392 + 403: 3x3 reversal tables of every gene against the genes with mask != 0, level k;
+ * table: r x 9 Int32 row-major (n11 n12 n13 n21 ... n33).  thresholds as above (NULL -> pval_reo). */
+int reo_tables(reo_handle_t h, int32_t k, const int32_t* thresholds, double pval_reo, const uint8_t* mask,
+               int32_t* table);
+/* Same result through the incremental path: build for mask_from, then apply the signed update
+ * over the symmetric difference to reach mask_to. */
+int reo_tables_delta(reo_handle_t h, int32_t k, const int32_t* thresholds, double pval_reo,
+                     const uint8_t* mask_from, const uint8_t* mask_to, int32_t* table);
+
+/* McCullagh_test, src:225-259, on the device: n tables of k x k Int64 (row-major) ->
+ * n x 5 doubles (pval d1 d2 se z1). */
+int reo_mccullagh(reo_handle_t h, const int64_t* tables, int64_t n, int32_t k, double* out);
+
+/* src:409-412: sort, trimmed std, two-sided normal p.  n > 10. */
+int reo_empirical_null(reo_handle_t h, const double* delta1, int64_t n, double* pval, double* se);
+/* src:413: Benjamini-Hochberg adjustment on the device. */
+int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj);
+/* ascending stable sort of doubles on the device (used by the two above); perm may be NULL. */
+int reo_sort_f64(reo_handle_t h, const double* x, int64_t n, double* sorted, int32_t* perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REO_H */

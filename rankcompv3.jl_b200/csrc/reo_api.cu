@@ -1,0 +1,691 @@
+// reo_api.cu -- the C ABI of libreo_cuda.so (include/reo.h) and the host orchestration of the
+// identify_degs loop (reference: src/RankCompV3.jl:339-438).  Host code only decides launches and
+// reads back three counters per evaluation; every number in the result is computed on the device.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "reo_internal.cuh"
+
+namespace {
+
+std::mutex g_err_mu;
+std::string g_create_err;
+
+template <typename T>
+struct DBuf {  // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct ReoDev {
+    int dev = 0;
+    int num_sms = 148;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {};
+    ReoStaged S;
+    DBuf<uint8_t> raw;
+    DBuf<uint16_t> ranks;
+    DBuf<uint32_t> planes, panel;
+    DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, counts,
+        fblist, small_i;
+    DBuf<int8_t> changed_sign, updown;
+    DBuf<uint8_t> mask_a, mask_b;
+    DBuf<double> result, sorted, sorted_p, se, small_d;
+    DBuf<unsigned int> counter;
+    DBuf<int> flags;
+    DBuf<unsigned long long> fb_keys;
+    DBuf<uint32_t> fb_rank;
+    DBuf<long long> small_ll;
+    ReoSortWs sortws;
+    int32_t* h_counts = nullptr;  // pinned
+    int table_rows = 0;           // rows allocated in `table`
+    std::vector<cudaEvent_t> pev; // event pairs bracketing every pair-kernel launch of the current call
+    int n_pev = 0;
+};
+
+struct reo_handle_s {
+    std::vector<ReoDev> devs;
+    uint64_t seed = 0;
+    std::string err;
+    int rank = 0, world = 1;
+    reo_allgather_fn ag_fn = nullptr;
+    void* ag_ctx = nullptr;
+    // launch accounting of the current call
+    int pair_launches = 0, kernel_launches = 0;
+    int64_t compares = 0;
+};
+
+namespace {
+
+int fail(reo_handle_t h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    else { std::lock_guard<std::mutex> g(g_err_mu); g_create_err = msg; }
+    return code;
+}
+int fail_cuda(reo_handle_t h, cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return fail(h, e == cudaErrorMemoryAllocation ? REO_ERR_OOM : REO_ERR_CUDA, m);
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t _e = (call);                                     \
+        if (_e != cudaSuccess) return fail_cuda(h, _e, #call);       \
+    } while (0)
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case REO_I64: case REO_F64: return 8;
+        case REO_I32: case REO_F32: return 4;
+        default: return 0;
+    }
+}
+
+// ---- get_major_reo_lower_count, src:81-92 (host; integer result) --------------------------------
+long double log_pmf_half(int n, int k) {
+    return lgammal((long double)n + 1) - lgammal((long double)k + 1) - lgammal((long double)(n - k) + 1)
+           - (long double)n * logl(2.0L);
+}
+long double cdf_half(int n, int x) {  // P[X <= x], X ~ Binomial(n, 1/2); terms decay going down from x <= n/2
+    if (x < 0) return 0.0L;
+    long double term = 1.0L, sum = 0.0L;
+    for (int k = x; k >= 0; --k) {
+        sum += term;
+        if (term < 1e-25L * sum) break;
+        term *= (long double)k / (long double)(n - k + 1);
+    }
+    return expl(log_pmf_half(n, x)) * sum;
+}
+long double two_sided_binom_p(int n, int x) {  // HypothesisTests.pvalue(Binomial(n), x), tail = :both
+    long double lo = cdf_half(n, x), hi = 1.0L - cdf_half(n, x - 1);
+    long double p = 2.0L * std::min(lo, hi);
+    return p > 1.0L ? 1.0L : p;
+}
+
+struct LevelPlan {  // the two-group view of level k
+    int WA = 0, nA = 0, nB = 0, padA = 0, padB = 0, thrA = 0, thrB = 0;
+    std::vector<int32_t> word_order;
+};
+
+LevelPlan make_plan(const ReoStaged& S, int k, const int32_t* thresholds, double pval_reo) {
+    LevelPlan P;
+    for (int w = 0; w < S.lev_words[k]; ++w) P.word_order.push_back(S.lev_word0[k] + w);
+    P.WA = S.lev_words[k];
+    for (int g = 0; g < S.gnum; ++g) {
+        if (g == k) continue;
+        for (int w = 0; w < S.lev_words[g]; ++w) P.word_order.push_back(S.lev_word0[g] + w);
+        P.padB += S.lev_words[g] * 32 - S.lev_n[g];
+    }
+    P.nA = S.lev_n[k];
+    P.nB = (int)S.c - P.nA;
+    P.padA = S.lev_words[k] * 32 - P.nA;
+    if (thresholds) { P.thrA = thresholds[0 + 2 * k]; P.thrB = thresholds[1 + 2 * k]; }
+    else { P.thrA = reo_threshold(P.nA, pval_reo); P.thrB = reo_threshold(P.nB, pval_reo); }
+    return P;
+}
+
+int upload_plan(reo_handle_t h, ReoDev& D, const LevelPlan& P) {
+    CK(D.word_order.ensure(P.word_order.size()));
+    CK(cudaMemcpyAsync(D.word_order.p, P.word_order.data(), P.word_order.size() * 4, cudaMemcpyHostToDevice, D.st));
+    return REO_OK;
+}
+
+// ---- K1 -----------------------------------------------------------------------------------------
+int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, const int32_t* group_id,
+             int32_t gnum, uint32_t flags) {
+    ReoDev& D = h->devs[0];
+    ReoStaged& S = D.S;
+    S.valid = false;
+    const size_t es = dtype_size(dtype);
+    if (!data || !group_id || es == 0 || r < 1 || c < 1 || ld < r) return fail(h, REO_ERR_ARG, "reo_stage: bad argument");
+    if (gnum < 2) return fail(h, REO_ERR_DIM, "Only 1 level in 'group', at least 2 levels!");
+    if (r > 65535) return fail(h, REO_ERR_UNSUPPORTED, "more than 65535 genes: uint16 dense ranks do not fit");
+    if (c > (int64_t)1 << 24) return fail(h, REO_ERR_UNSUPPORTED, "more than 2^24 samples");
+    std::vector<int> lev_n(gnum, 0);
+    for (int64_t s = 0; s < c; ++s) {
+        if (group_id[s] < 0 || group_id[s] >= gnum) return fail(h, REO_ERR_DIM, "group_id out of range");
+        lev_n[group_id[s]]++;
+    }
+    for (int g = 0; g < gnum; ++g)
+        if (lev_n[g] == 0) return fail(h, REO_ERR_DIM, "empty group level");
+    CK(cudaSetDevice(D.dev));
+    S.r = r; S.c = c; S.gnum = gnum;
+    S.NT = (int)((r + REO_TILE - 1) / REO_TILE);
+    S.lev_n = lev_n;
+    S.lev_words.assign(gnum, 0); S.lev_word0.assign(gnum, 0);
+    int W = 0;
+    for (int g = 0; g < gnum; ++g) { S.lev_word0[g] = W; S.lev_words[g] = (lev_n[g] + 31) / 32; W += S.lev_words[g]; }
+    S.W = W;
+    const int64_t nslots = (int64_t)W * 32;
+    const int64_t rpad = (int64_t)S.NT * REO_TILE;
+    std::vector<int32_t> slot_of_sample(c), sample_of_slot(nslots, -1);
+    {
+        std::vector<int> fill(gnum, 0);
+        for (int64_t s = 0; s < c; ++s) {
+            const int g = group_id[s];
+            const int32_t slot = S.lev_word0[g] * 32 + fill[g]++;
+            slot_of_sample[s] = slot; sample_of_slot[slot] = (int32_t)s;
+        }
+    }
+    CK(D.slot_of_sample.ensure(c));
+    CK(D.sample_of_slot.ensure(nslots));
+    CK(cudaMemcpyAsync(D.slot_of_sample.p, slot_of_sample.data(), c * 4, cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemcpyAsync(D.sample_of_slot.p, sample_of_slot.data(), nslots * 4, cudaMemcpyHostToDevice, D.st));
+    CK(D.ranks.ensure((size_t)nslots * rpad));
+    CK(cudaMemsetAsync(D.ranks.p, 0, (size_t)nslots * rpad * sizeof(uint16_t), D.st));
+    CK(D.flags.ensure(4));
+    CK(cudaMemsetAsync(D.flags.p, 0, 4 * sizeof(int), D.st));
+    CK(D.fblist.ensure(c));
+
+    // raw matrix: already on the device, or copied in column chunks that overlap with ranking
+    const uint8_t* dev_data = (const uint8_t*)data;
+    int64_t dev_ld = ld;
+    if (!(flags & REO_DATA_ON_DEVICE)) {
+        CK(D.raw.ensure((size_t)r * c * es));
+        dev_data = D.raw.p; dev_ld = r;
+    }
+    int64_t chunk = std::max<int64_t>(32, (int64_t)(16u << 20) / (int64_t)(r * es));
+    chunk = (chunk + 31) / 32 * 32;
+    for (int64_t c0 = 0; c0 < c; c0 += chunk) {
+        const int64_t nc = std::min(chunk, c - c0);
+        if (!(flags & REO_DATA_ON_DEVICE)) {
+            CK(cudaMemcpy2DAsync(D.raw.p + (size_t)c0 * r * es, (size_t)r * es, (const uint8_t*)data + (size_t)c0 * ld * es,
+                                 (size_t)ld * es, (size_t)r * es, (size_t)nc, cudaMemcpyHostToDevice, D.st));
+        }
+        CK(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, c0, (int)nc, D.slot_of_sample.p, D.ranks.p, rpad,
+                                   D.flags.p + 2, D.flags.p, D.fblist.p, D.st));
+        h->kernel_launches++;
+    }
+    CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    if (D.h_counts[0])
+        return fail(h, REO_ERR_UNSUPPORTED,
+                    "non-integral expression values: the 0.1 tie band of is_greater (src:72) is not rank-"
+                    "compressible; the float path is not built yet");
+    const int nfb = D.h_counts[1];
+    if (nfb > 0) {
+        int64_t rp2 = 1;
+        while (rp2 < r) rp2 <<= 1;
+        const int batch = std::min(nfb, 2 * D.num_sms);
+        CK(D.fb_keys.ensure((size_t)batch * rp2));
+        CK(D.fb_rank.ensure((size_t)batch * rp2));
+        for (int b0 = 0; b0 < nfb; b0 += batch) {
+            const int nb = std::min(batch, nfb - b0);
+            CK(reo_launch_rank_fallback(dev_data, dtype, r, dev_ld, D.fblist.p + b0, nb, D.slot_of_sample.p, D.ranks.p,
+                                        rpad, D.flags.p + 2, D.fb_keys.p, D.fb_rank.p, rp2, D.st));
+            h->kernel_launches++;
+        }
+        CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
+    }
+    const int distinct = std::max(D.h_counts[2], 1);
+    int B = 1;
+    while ((1 << B) < distinct) ++B;
+    if (B > REO_MAX_BITS) return fail(h, REO_ERR_UNSUPPORTED, "rank needs more than 16 bits");
+    S.B = B; S.NP = B + 1;
+    CK(D.planes.ensure((size_t)S.NT * S.tile_stride()));
+    S.planes = D.planes.p;
+    CK(reo_launch_bitplanes(D.ranks.p, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
+                            (uint32_t)(h->seed >> 32), S.planes, D.st));
+    h->kernel_launches++;
+    // identity column list for "all genes are references"
+    {
+        std::vector<int32_t> iota(rpad, -1);
+        for (int64_t i = 0; i < r; ++i) iota[i] = (int32_t)i;
+        CK(D.iota.ensure(rpad));
+        CK(cudaMemcpyAsync(D.iota.p, iota.data(), rpad * 4, cudaMemcpyHostToDevice, D.st));
+        CK(cudaStreamSynchronize(D.st));  // iota is a host temporary
+    }
+    CK(D.col_gene.ensure(rpad));
+    CK(D.changed_gene.ensure(rpad));
+    CK(D.changed_sign.ensure(rpad));
+    CK(D.counts.ensure(8));
+    CK(D.counter.ensure(1));
+    CK(D.mask_a.ensure(r));
+    CK(D.mask_b.ensure(r));
+    // table: world * tiles_per_rank * 64 rows so that the all-gather slices are equal
+    const int tpr = (S.NT + h->world - 1) / h->world;
+    D.table_rows = h->world * tpr * REO_TILE;
+    CK(D.table.ensure((size_t)D.table_rows * 9));
+    S.valid = true;
+    return REO_OK;
+}
+
+// ---- K2 launches --------------------------------------------------------------------------------
+// Accumulate sign * category counts of every row gene of this rank's shard against `ncols` panel
+// columns listed (ascending, padded to 64 with -1) in col_gene_dev.
+int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* col_gene_dev,
+                  const int8_t* col_sign_dev, int ncols, bool all_genes) {
+    const ReoStaged& S = D.S;
+    if (ncols <= 0) return REO_OK;
+    const int ntc = (ncols + REO_TILE - 1) / REO_TILE;
+    const uint32_t* colp = S.planes;
+    if (!all_genes) {
+        CK(D.panel.ensure((size_t)ntc * S.tile_stride()));
+        CK(reo_launch_gather_panel(S.planes, S.W, S.NP, col_gene_dev, ntc, D.panel.p, D.st));
+        h->kernel_launches++;
+        colp = D.panel.p;
+    }
+    const int tpr = (S.NT + h->world - 1) / h->world;
+    ReoPairParams p;
+    memset(&p, 0, sizeof(p));
+    p.row_planes = S.planes; p.col_planes = colp; p.col_gene = col_gene_dev; p.col_sign = col_sign_dev;
+    p.word_order = D.word_order.p; p.table = D.table.p; p.counter = D.counter.p;
+    p.W = S.W; p.WA = P.WA; p.NP = S.NP; p.r = (int)S.r;
+    p.t0 = std::min(S.NT, h->rank * tpr); p.t1 = std::min(S.NT, (h->rank + 1) * tpr);
+    p.ntc = ntc;
+    const int ntr = p.t1 - p.t0;
+    if (ntr <= 0) return REO_OK;
+    const int want_items = 8 * 2 * D.num_sms;
+    int njc = std::max(1, std::min(ntc, (want_items + ntr - 1) / ntr));
+    p.jchunk = (ntc + njc - 1) / njc;
+    p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;
+    p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
+    CK(cudaMemsetAsync(D.counter.p, 0, sizeof(unsigned int), D.st));
+    if ((size_t)(2 * D.n_pev + 2) > D.pev.size()) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        D.pev.push_back(a); D.pev.push_back(b);
+    }
+    CK(cudaEventRecord(D.pev[2 * D.n_pev], D.st));
+    CK(reo_launch_pairs(p, D.num_sms, D.st));
+    CK(cudaEventRecord(D.pev[2 * D.n_pev + 1], D.st));
+    D.n_pev++;
+    h->pair_launches++; h->kernel_launches++;
+    const int64_t rows = std::min<int64_t>(S.r, (int64_t)p.t1 * REO_TILE) - (int64_t)p.t0 * REO_TILE;
+    h->compares += std::max<int64_t>(rows, 0) * (int64_t)ncols * S.c;
+    return REO_OK;
+}
+
+// full build for the mask in mask_dev
+int build_tables_full(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* mask_dev) {
+    const ReoStaged& S = D.S;
+    CK(reo_launch_mask_to_list(mask_dev, S.r, D.col_gene.p, D.counts.p + 4, D.st));
+    h->kernel_launches++;
+    CK(cudaMemcpyAsync(D.h_counts + 4, D.counts.p + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+    CK(cudaMemsetAsync(D.table.p, 0, (size_t)D.table_rows * 9 * sizeof(int32_t), D.st));
+    CK(cudaStreamSynchronize(D.st));
+    const int ncols = D.h_counts[4];
+    const bool all = (ncols == (int)S.r);
+    return launch_tables(h, D, P, all ? D.iota.p : D.col_gene.p, nullptr, ncols, all);
+}
+
+int allgather_tables(reo_handle_t h, ReoDev& D) {
+    if (h->world <= 1) return REO_OK;
+    if (!h->ag_fn) return fail(h, REO_ERR_COMM, "world > 1 but no all-gather callback set");
+    CK(cudaStreamSynchronize(D.st));
+    const uint64_t bytes = (uint64_t)(D.table_rows / h->world) * 9 * sizeof(int32_t);
+    if (h->ag_fn(h->ag_ctx, D.table.p, bytes) != 0) return fail(h, REO_ERR_COMM, "all-gather callback failed");
+    return REO_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int reo_version(void) { return REO_VERSION; }
+
+const char* reo_last_error(reo_handle_t h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mu);
+    return g_create_err.c_str();
+}
+
+int reo_create(reo_handle_t* out, int ndev, const int* devs, uint64_t seed, uint32_t /*flags*/) {
+    if (!out || ndev < 1) return fail(nullptr, REO_ERR_ARG, "reo_create: bad argument");
+    if (ndev > 1)
+        return fail(nullptr, REO_ERR_UNSUPPORTED,
+                    "single-process multi-GPU is not built yet: use one process per GPU with reo_set_collective");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1) {
+        cudaGetLastError();
+        return fail(nullptr, REO_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    reo_handle_s* h = new (std::nothrow) reo_handle_s();
+    if (!h) return fail(nullptr, REO_ERR_OOM, "host allocation failed");
+    h->seed = seed;
+    h->devs.resize(ndev);
+    for (int i = 0; i < ndev; ++i) {
+        ReoDev& D = h->devs[i];
+        D.dev = devs ? devs[i] : i;
+        if (D.dev < 0 || D.dev >= count) { delete h; return fail(nullptr, REO_ERR_ARG, "reo_create: bad device index"); }
+        if ((e = cudaSetDevice(D.dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete h; cudaGetLastError();
+            return fail(nullptr, REO_ERR_CUDA, std::string("reo_create: ") + cudaGetErrorString(e));
+        }
+        cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, D.dev);
+        for (auto& ev : D.ev) cudaEventCreate(&ev);
+        if (cudaMallocHost((void**)&D.h_counts, 16 * sizeof(int32_t)) != cudaSuccess) {
+            delete h; cudaGetLastError();
+            return fail(nullptr, REO_ERR_OOM, "pinned allocation failed");
+        }
+    }
+    *out = h;
+    return REO_OK;
+}
+
+int reo_destroy(reo_handle_t h) {
+    if (!h) return REO_OK;
+    for (ReoDev& D : h->devs) {
+        cudaSetDevice(D.dev);
+        if (D.st) cudaStreamSynchronize(D.st);
+        D.raw.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
+        D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
+        D.changed_gene.release(); D.table.release(); D.perm.release(); D.counts.release(); D.fblist.release();
+        D.small_i.release(); D.changed_sign.release(); D.updown.release(); D.mask_a.release(); D.mask_b.release();
+        D.result.release(); D.sorted.release(); D.sorted_p.release(); D.se.release(); D.small_d.release();
+        D.counter.release(); D.flags.release(); D.fb_keys.release(); D.fb_rank.release(); D.small_ll.release();
+        if (D.sortws.keys) cudaFree(D.sortws.keys);
+        if (D.sortws.idx) cudaFree(D.sortws.idx);
+        if (D.h_counts) cudaFreeHost(D.h_counts);
+        for (auto& ev : D.ev) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : D.pev) cudaEventDestroy(ev);
+        if (D.st) cudaStreamDestroy(D.st);
+    }
+    delete h;
+    return REO_OK;
+}
+
+int reo_set_collective(reo_handle_t h, int rank, int world, reo_allgather_fn fn, void* ctx) {
+    if (!h) return REO_ERR_ARG;
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return fail(h, REO_ERR_ARG, "reo_set_collective: bad argument");
+    h->rank = rank; h->world = world; h->ag_fn = fn; h->ag_ctx = ctx;
+    h->devs[0].S.valid = false;  // table sizing depends on world
+    return REO_OK;
+}
+
+int reo_threshold(int n, double pval) {
+    if (n < 0) return -1;
+    // pval_min = pvalue(Binomial(n), 0) = min(1, 2 * 2^-n)   (src:83)
+    long double pmin = ldexpl(1.0L, 1 - n);
+    if (pmin > 1.0L) pmin = 1.0L;
+    if (!(pmin < (long double)pval)) return n;  // warn path, src:88-90
+    // p(x) is non-decreasing on 0..floor(n/2): binary search the first x with p(x) > pval (src:85)
+    int lo = 0, hi = n / 2;
+    if (!(two_sided_binom_p(n, hi) > (long double)pval)) return -1;  // findfirst -> nothing
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (two_sided_binom_p(n, mid) > (long double)pval) hi = mid; else lo = mid + 1;
+    }
+    return n - lo + 1;
+}
+
+int reo_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, const int32_t* group_id,
+              int32_t gnum, uint32_t flags) {
+    if (!h) return REO_ERR_ARG;
+    h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0;
+    h->devs[0].n_pev = 0;
+    return do_stage(h, data, dtype, r, c, ld, group_id, gnum, flags);
+}
+
+int reo_stage_info(reo_handle_t h, int32_t* rank_bits, int32_t* sample_words, int32_t* gene_tiles) {
+    if (!h) return REO_ERR_ARG;
+    const ReoStaged& S = h->devs[0].S;
+    if (!S.valid) return fail(h, REO_ERR_STATE, "no staged matrix");
+    if (rank_bits) *rank_bits = S.B;
+    if (sample_words) *sample_words = S.W;
+    if (gene_tiles) *gene_tiles = S.NT;
+    return REO_OK;
+}
+
+int reo_pair_counts(reo_handle_t h, int32_t k, const int32_t* rows, int32_t nrows, const int32_t* cols, int32_t ncols,
+                    int32_t* nre, int32_t* rest) {
+    if (!h) return REO_ERR_ARG;
+    ReoDev& D = h->devs[0];
+    const ReoStaged& S = D.S;
+    if (!S.valid) return fail(h, REO_ERR_STATE, "no staged matrix");
+    if (!rows || !cols || !nre || !rest || nrows < 1 || ncols < 1 || k < 0 || k >= S.gnum)
+        return fail(h, REO_ERR_ARG, "reo_pair_counts: bad argument");
+    for (int i = 0; i < nrows; ++i) if (rows[i] < 0 || rows[i] >= S.r) return fail(h, REO_ERR_ARG, "row index out of range");
+    for (int i = 0; i < ncols; ++i) if (cols[i] < 0 || cols[i] >= S.r) return fail(h, REO_ERR_ARG, "col index out of range");
+    CK(cudaSetDevice(D.dev));
+    int32_t thr_dummy[128] = {0};
+    LevelPlan P = make_plan(S, k, S.gnum <= 64 ? thr_dummy : nullptr, 0.01);
+    int rc = upload_plan(h, D, P);
+    if (rc) return rc;
+    const size_t n = (size_t)nrows * ncols;
+    CK(D.small_i.ensure(nrows + ncols + 2 * n));
+    int32_t* d_rows = D.small_i.p; int32_t* d_cols = d_rows + nrows; int32_t* d_nre = d_cols + ncols; int32_t* d_rest = d_nre + n;
+    CK(cudaMemcpyAsync(d_rows, rows, nrows * 4, cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemcpyAsync(d_cols, cols, ncols * 4, cudaMemcpyHostToDevice, D.st));
+    CK(reo_launch_pair_counts_small(S, D.word_order.p, P.WA, d_rows, nrows, d_cols, ncols, d_nre, d_rest, P.padA, P.padB, D.st));
+    CK(cudaMemcpyAsync(nre, d_nre, n * 4, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaMemcpyAsync(rest, d_rest, n * 4, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+int reo_tables_delta(reo_handle_t h, int32_t k, const int32_t* thresholds, double pval_reo, const uint8_t* mask_from,
+                     const uint8_t* mask_to, int32_t* table) {
+    if (!h) return REO_ERR_ARG;
+    ReoDev& D = h->devs[0];
+    const ReoStaged& S = D.S;
+    if (!S.valid) return fail(h, REO_ERR_STATE, "no staged matrix");
+    if (!mask_from || !table || k < 0 || k >= S.gnum) return fail(h, REO_ERR_ARG, "reo_tables: bad argument");
+    CK(cudaSetDevice(D.dev));
+    LevelPlan P = make_plan(S, k, thresholds, pval_reo);
+    int rc = upload_plan(h, D, P);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(D.mask_a.p, mask_from, S.r, cudaMemcpyHostToDevice, D.st));
+    if ((rc = build_tables_full(h, D, P, D.mask_a.p))) return rc;
+    if (mask_to) {
+        CK(cudaMemcpyAsync(D.mask_b.p, mask_to, S.r, cudaMemcpyHostToDevice, D.st));
+        CK(reo_launch_mask_diff(S.r, D.mask_a.p, D.mask_b.p, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
+        CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
+        if ((rc = launch_tables(h, D, P, D.changed_gene.p, D.changed_sign.p, D.h_counts[2], false))) return rc;
+    }
+    if ((rc = allgather_tables(h, D))) return rc;
+    CK(cudaMemcpyAsync(table, D.table.p, (size_t)S.r * 9 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+int reo_tables(reo_handle_t h, int32_t k, const int32_t* thresholds, double pval_reo, const uint8_t* mask,
+               int32_t* table) {
+    return reo_tables_delta(h, k, thresholds, pval_reo, mask, nullptr, table);
+}
+
+int reo_mccullagh(reo_handle_t h, const int64_t* tables, int64_t n, int32_t k, double* out) {
+    if (!h) return REO_ERR_ARG;
+    ReoDev& D = h->devs[0];
+    if (!tables || !out || n < 1 || k < 2 || k > 9) return fail(h, REO_ERR_ARG, "reo_mccullagh: bad argument");
+    CK(cudaSetDevice(D.dev));
+    CK(D.small_ll.ensure((size_t)n * k * k));
+    CK(D.small_d.ensure((size_t)n * 5));
+    CK(cudaMemcpyAsync(D.small_ll.p, tables, (size_t)n * k * k * 8, cudaMemcpyHostToDevice, D.st));
+    CK(reo_launch_mccullagh_kxk((const int64_t*)D.small_ll.p, n, k, D.small_d.p, D.st));
+    CK(cudaMemcpyAsync(out, D.small_d.p, (size_t)n * 5 * 8, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+int reo_sort_f64(reo_handle_t h, const double* x, int64_t n, double* sorted, int32_t* perm) {
+    if (!h) return REO_ERR_ARG;
+    ReoDev& D = h->devs[0];
+    if (!x || !sorted || n < 1) return fail(h, REO_ERR_ARG, "reo_sort_f64: bad argument");
+    CK(cudaSetDevice(D.dev));
+    CK(D.small_d.ensure((size_t)2 * n));
+    CK(D.perm.ensure(n));
+    CK(cudaMemcpyAsync(D.small_d.p, x, n * 8, cudaMemcpyHostToDevice, D.st));
+    CK(reo_launch_sort_f64(D.small_d.p, n, D.small_d.p + n, D.perm.p, D.sortws, D.st));
+    CK(cudaMemcpyAsync(sorted, D.small_d.p + n, n * 8, cudaMemcpyDeviceToHost, D.st));
+    if (perm) CK(cudaMemcpyAsync(perm, D.perm.p, n * 4, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+int reo_empirical_null(reo_handle_t h, const double* delta1, int64_t n, double* pval, double* se) {
+    if (!h) return REO_ERR_ARG;
+    ReoDev& D = h->devs[0];
+    if (!delta1 || !pval || n < 1) return fail(h, REO_ERR_ARG, "reo_empirical_null: bad argument");
+    if (n <= 10) return fail(h, REO_ERR_BOUNDS, "BoundsError: r <= 10 (src:411)");
+    CK(cudaSetDevice(D.dev));
+    CK(D.small_d.ensure((size_t)3 * n + 1));
+    double* d_x = D.small_d.p; double* d_s = d_x + n; double* d_p = d_s + n; double* d_se = d_p + n;
+    CK(cudaMemcpyAsync(d_x, delta1, n * 8, cudaMemcpyHostToDevice, D.st));
+    CK(reo_launch_sort_f64(d_x, n, d_s, nullptr, D.sortws, D.st));
+    CK(reo_launch_trimmed_std(d_s, n, d_se, nullptr, D.st));
+    CK(reo_launch_null_pvals(d_x, n, d_se, d_p, D.st));
+    CK(cudaMemcpyAsync(pval, d_p, n * 8, cudaMemcpyDeviceToHost, D.st));
+    if (se) CK(cudaMemcpyAsync(se, d_se, 8, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj) {
+    if (!h) return REO_ERR_ARG;
+    ReoDev& D = h->devs[0];
+    if (!p || !padj || n < 1) return fail(h, REO_ERR_ARG, "reo_bh: bad argument");
+    CK(cudaSetDevice(D.dev));
+    CK(D.small_d.ensure((size_t)3 * n));
+    CK(D.perm.ensure(n));
+    double* d_x = D.small_d.p; double* d_s = d_x + n; double* d_q = d_s + n;
+    CK(cudaMemcpyAsync(d_x, p, n * 8, cudaMemcpyHostToDevice, D.st));
+    if (n > 1) {
+        CK(reo_launch_sort_f64(d_x, n, d_s, D.perm.p, D.sortws, D.st));
+        CK(reo_launch_bh(d_s, D.perm.p, n, d_q, nullptr, D.st));
+    } else {
+        d_q = d_x;
+    }
+    CK(cudaMemcpyAsync(padj, d_q, n * 8, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld,
+                      const int32_t* group_id, int32_t gnum, const int32_t* thresholds, double pval_reo,
+                      double pval_deg, double padj_deg, const uint8_t* ref_mask, int32_t n_iter, int32_t n_conv,
+                      uint32_t flags, double* result, int8_t* updown, uint8_t* final_ref, int32_t* iters_done,
+                      reo_stats* stats) {
+    if (!h) return REO_ERR_ARG;
+    if (!data || !group_id || !ref_mask || !result || !updown) return fail(h, REO_ERR_ARG, "reo_identify_degs: NULL argument");
+    if (gnum < 2) return fail(h, REO_ERR_DIM, "Only 1 level in 'group', at least 2 levels!");
+    if (r <= 10) return fail(h, REO_ERR_BOUNDS, "BoundsError: r <= 10 (src:411)");
+    ReoDev& D = h->devs[0];
+    CK(cudaSetDevice(D.dev));
+    h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0;
+    cudaEvent_t e_start = D.ev[0], e_staged = D.ev[1], e_end = D.ev[2];
+    D.n_pev = 0;
+    CK(cudaEventRecord(e_start, D.st));
+    int rc = do_stage(h, data, dtype, r, c, ld, group_id, gnum, flags);
+    if (rc) return rc;
+    CK(cudaEventRecord(e_staged, D.st));
+    const ReoStaged& S = D.S;
+    const int K = gnum == 2 ? 1 : gnum;
+    CK(D.result.ensure((size_t)r * 15));
+    CK(D.sorted.ensure(r)); CK(D.sorted_p.ensure(r)); CK(D.perm.ensure(r)); CK(D.se.ensure(1)); CK(D.updown.ensure(r));
+    reo_stats st_local;
+    memset(&st_local, 0, sizeof(st_local));
+    double ms_pairs = 0.0;
+    // results are assembled in host temporaries so that caller outputs stay untouched on failure
+    std::vector<double> res_host((size_t)K * r * 15);
+    std::vector<int8_t> ud_host((size_t)K * r);
+    std::vector<uint8_t> fr_host((size_t)K * r);
+    std::vector<int32_t> it_host(K, 0);
+
+    for (int k = 0; k < K; ++k) {
+        LevelPlan P = make_plan(S, k, thresholds, pval_reo);
+        if ((rc = upload_plan(h, D, P))) return rc;
+        uint8_t* mask_cur = D.mask_a.p;
+        uint8_t* mask_new = D.mask_b.p;
+        CK(cudaMemcpyAsync(mask_cur, ref_mask, r, cudaMemcpyHostToDevice, D.st));
+        CK(cudaMemsetAsync(D.result.p, 0, (size_t)r * 15 * sizeof(double), D.st));
+        int i_iter = 0, n_eval = 0, converged = 0;
+        bool have_tables = false;
+        while (i_iter < n_iter) {
+            if (!have_tables) {
+                if ((rc = build_tables_full(h, D, P, mask_cur))) return rc;
+                have_tables = true;
+            }
+            if ((rc = allgather_tables(h, D))) return rc;
+            // src:402-406
+            CK(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
+            // src:409-412
+            CK(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, nullptr, D.sortws, D.st));
+            CK(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, nullptr, D.st));
+            CK(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));
+            // src:413
+            CK(reo_launch_sort_f64(D.result.p, r, D.sorted_p.p, D.perm.p, D.sortws, D.st));
+            CK(reo_launch_bh(D.sorted_p.p, D.perm.p, r, D.result.p + r, nullptr, D.st));
+            // src:417
+            CK(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));
+            CK(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
+            h->kernel_launches += 10;
+            CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+            CK(cudaStreamSynchronize(D.st));
+            const int n_ref = D.h_counts[0], n_inds = D.h_counts[1], n_chg = D.h_counts[2];
+            if (n_eval < REO_MAX_ITER_LOG) { st_local.n_deg[n_eval] = (int32_t)r - n_inds; st_local.n_ref[n_eval] = n_ref; }
+            n_eval++;
+            if (abs(n_ref - n_inds) < n_conv) {  // src:419-422
+                converged = 1;
+                break;
+            }
+            i_iter++;
+            if (i_iter < n_iter) {
+                // tables for the new reference set: signed update over the symmetric difference when
+                // that is cheaper than a rebuild (the G x G categories are never stored)
+                if (n_chg < n_inds) {
+                    if ((rc = launch_tables(h, D, P, D.changed_gene.p, D.changed_sign.p, n_chg, false))) return rc;
+                    std::swap(mask_cur, mask_new);
+                } else {
+                    std::swap(mask_cur, mask_new);
+                    if ((rc = build_tables_full(h, D, P, mask_cur))) return rc;
+                }
+            }
+        }
+        if (n_eval == 0) CK(cudaMemsetAsync(D.result.p, 0, (size_t)r * 15 * sizeof(double), D.st));
+        CK(reo_launch_updown(D.result.p, r, pval_deg, padj_deg, D.updown.p, D.st));
+        h->kernel_launches++;
+        CK(cudaMemcpyAsync(res_host.data() + (size_t)k * r * 15, D.result.p, (size_t)r * 15 * 8, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(ud_host.data() + (size_t)k * r, D.updown.p, r, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(fr_host.data() + (size_t)k * r, mask_cur, r, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
+        it_host[k] = n_eval;
+        st_local.iters_done = n_eval; st_local.converged = converged;
+    }
+    CK(cudaEventRecord(e_end, D.st));
+    CK(cudaEventSynchronize(e_end));
+    float ms_stage = 0, ms_total = 0;
+    cudaEventElapsedTime(&ms_stage, e_start, e_staged);
+    cudaEventElapsedTime(&ms_total, e_start, e_end);
+    for (int i = 0; i < D.n_pev; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, D.pev[2 * i], D.pev[2 * i + 1]);
+        ms_pairs += ms;
+    }
+    memcpy(result, res_host.data(), res_host.size() * 8);
+    memcpy(updown, ud_host.data(), ud_host.size());
+    if (final_ref) memcpy(final_ref, fr_host.data(), fr_host.size());
+    if (iters_done) memcpy(iters_done, it_host.data(), K * sizeof(int32_t));
+    if (stats) {
+        st_local.rank_bits = S.B; st_local.sample_words = S.W; st_local.compares = h->compares;
+        st_local.ms_stage = ms_stage; st_local.ms_pairs = ms_pairs; st_local.ms_total = ms_total;
+        st_local.ms_stats = ms_total - ms_stage - ms_pairs;
+        st_local.pair_launches = h->pair_launches; st_local.kernel_launches = h->kernel_launches;
+        *stats = st_local;
+    }
+    return REO_OK;
+}
+
+}  // extern "C"

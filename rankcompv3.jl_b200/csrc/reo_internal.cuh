@@ -1,0 +1,115 @@
+// reo_internal.cuh -- shared declarations of libreo_cuda.so (not part of the C ABI).
+//
+// Data layout in HBM:
+//   planes[t][w][p][l]  uint32, t = gene tile (64 genes), w = sample word (32 samples of ONE group
+//   level, levels padded to a multiple of 32), p = bit-plane (p = 0: tie-coin bits u(i,s);
+//   p = 1..B: bits of the per-sample dense rank, LSB first), l = gene within the tile.
+//   Bit `b` of a word is sample slot 32*w + b.  Pad slots and pad genes are all-zero.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "reo.h"
+
+#define REO_TILE 64            // genes per tile
+#define REO_MAX_BITS 16        // rank bits (u16 ranks)
+#define REO_MAX_PLANES (REO_MAX_BITS + 1)
+
+// ---- tie coin: must match oracle/reo_oracle.{py,c} bit for bit --------------------------------
+__host__ __device__ __forceinline__ uint32_t reo_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t reo_coin_u(uint32_t seed_lo, uint32_t seed_hi, uint32_t gene,
+                                                        uint32_t sample) {
+    uint32_t h = reo_mix32(seed_lo ^ (gene * 0x9E3779B1u));
+    h = reo_mix32(h + sample * 0x85EBCA77u + seed_hi);
+    return h >> 31;
+}
+
+// ---- staged matrix ------------------------------------------------------------------------------
+struct ReoStaged {
+    int64_t r = 0, c = 0;
+    int gnum = 0;
+    int NT = 0;        // gene tiles
+    int W = 0;         // sample words (all levels)
+    int B = 0;         // rank bits
+    int NP = 0;        // planes = B + 1
+    uint32_t* planes = nullptr;      // [NT][W][NP][64]
+    std::vector<int> lev_word0;      // first word of each level
+    std::vector<int> lev_words;      // words of each level
+    std::vector<int> lev_n;          // real samples of each level
+    bool valid = false;
+    size_t word_stride() const { return (size_t)NP * REO_TILE; }
+    size_t tile_stride() const { return (size_t)W * NP * REO_TILE; }
+};
+
+// ---- pair kernel parameters ---------------------------------------------------------------------
+struct ReoPairParams {
+    const uint32_t* row_planes;  // [NT][W][NP][64]
+    const uint32_t* col_planes;  // [NTc][W][NP][64] (panel of compacted columns, may alias row_planes)
+    const int32_t* col_gene;     // [NTc*64] gene index of each panel column, -1 = pad
+    const int8_t* col_sign;      // [NTc*64] +1/-1 (nullptr -> +1)
+    const int32_t* word_order;   // [W]: the first WA entries are the words of group A (level k)
+    int32_t* table;              // [.. ][9] Int32, += sign per (row gene, category)
+    unsigned int* counter;       // dynamic work counter (zeroed before launch)
+    int W, WA, NP;
+    int r;                       // real genes
+    int t0, t1;                  // row tile range [t0, t1)
+    int ntc;                     // column tiles in the panel
+    int jchunk, njchunks;        // column tiles per work item, items per row tile
+    int nA, nB, padA, padB, thrA, thrB;
+    unsigned long long* compares;  // optional (nullptr): not used by the kernel
+};
+
+// kernels / launchers implemented in the .cu files
+struct ReoDev;  // per-device state (reo_api.cu)
+
+cudaError_t reo_launch_pairs(const ReoPairParams& p, int num_sms, cudaStream_t st);
+cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word_order, int WA, const int32_t* rows,
+                                         int nrows, const int32_t* cols, int ncols, int32_t* nre, int32_t* rest,
+                                         int padA, int padB, cudaStream_t st);
+
+// staging (reo_stage.cu)
+cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
+                                    const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                    int* max_distinct, int* flags /*[0]=nonintegral,[1]=n_fallback*/,
+                                    int32_t* fallback_list, cudaStream_t st);
+cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* fallback_list,
+                                     int nfb, const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                     int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank,
+                                     int64_t rpow2, cudaStream_t st);
+cudaError_t reo_launch_bitplanes(const uint16_t* ranks, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
+                                 int NT, int W, int NP, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes,
+                                 cudaStream_t st);
+cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const int32_t* col_gene, int ntc,
+                                    uint32_t* panel, cudaStream_t st);
+
+// statistics (reo_stats.cu)
+cudaError_t reo_launch_mccullagh_tables(const int32_t* table, int64_t r, double* result /*col-major r x 15*/,
+                                        cudaStream_t st);
+cudaError_t reo_launch_mccullagh_kxk(const int64_t* tables, int64_t n, int k, double* out, cudaStream_t st);
+struct ReoSortWs {  // workspace for reo_sort
+    unsigned long long* keys = nullptr;  // chunk-sorted keys
+    uint32_t* idx = nullptr;
+    int64_t cap = 0;
+};
+cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,
+                                cudaStream_t st);
+cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* leaf_ws, cudaStream_t st);
+cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se, double* pval, cudaStream_t st);
+cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* ws,
+                          cudaStream_t st);
+// inds = !(p<=pd && q<=qd) (src:417)
+cudaError_t reo_launch_inds(const double* pval, const double* padj, int64_t r, double pval_deg, double padj_deg,
+                            uint8_t* mask_new, cudaStream_t st);
+// counts[0]=sum(old) counts[1]=sum(new) counts[2]=n_changed; changed_gene/changed_sign = ascending list over
+// old xor new (padded to a multiple of 64 with -1/0)
+cudaError_t reo_launch_mask_diff(int64_t r, const uint8_t* mask_old, const uint8_t* mask_new, int32_t* counts,
+                                 int32_t* changed_gene, int8_t* changed_sign, cudaStream_t st);
+// compaction of a mask into an ascending column list (padded to a multiple of 64 with -1); counts[0]=n
+cudaError_t reo_launch_mask_to_list(const uint8_t* mask, int64_t r, int32_t* list, int32_t* count, cudaStream_t st);
+cudaError_t reo_launch_updown(const double* result, int64_t r, double pval_deg, double padj_deg, int8_t* updown,
+                              cudaStream_t st);

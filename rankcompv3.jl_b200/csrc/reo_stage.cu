@@ -1,0 +1,324 @@
+// reo_stage.cu -- K1: staging of the expression matrix for the pair kernel.
+//
+// Reference semantics being prepared (src/RankCompV3.jl): the pair loop only ever evaluates
+// is_greater(data[i,s], data[j,s]) (src:71-77, 372) for two genes in the SAME sample, and for
+// integer-valued data the tie band |x-y| < 0.1 is exactly x == y.  So each sample column can be
+// replaced by its dense rank over genes (ties share a rank) without changing any REO.  Ranks are
+// then bit-sliced: 32 samples of one group level per 32-bit word, one word per rank bit, so the
+// pair kernel compares 32 samples per LOP3.  Plane 0 carries the tie-coin bits u(i,s).
+//
+// Kernels: rank_columns_kernel (bitmap dense rank, one CTA per sample), rank_fallback_kernel
+// (sort-based dense rank for columns whose value range exceeds the bitmap), bitplanes_kernel
+// (32 x B bit transpose + coin plane), gather_panel_kernel (compacts reference-gene columns).
+// All are HBM/L2-bound streaming passes; algorithmic bytes are stated in DESIGN.md.
+#include <limits.h>
+
+#include "reo_internal.cuh"
+
+#define RK_THREADS 1024
+#define BM_WORDS 40960                  // bitmap words in shared memory (1,310,720 distinct values)
+#define BM_GROUP 8                      // words per prefix entry
+#define BM_PRE (BM_WORDS / BM_GROUP)    // 5120 prefix entries
+#define BM_ITEMS ((BM_PRE + RK_THREADS - 1) / RK_THREADS)
+
+template <typename T>
+__device__ __forceinline__ bool to_ll(T v, long long& out);
+template <>
+__device__ __forceinline__ bool to_ll<long long>(long long v, long long& out) { out = v; return true; }
+template <>
+__device__ __forceinline__ bool to_ll<int>(int v, long long& out) { out = v; return true; }
+template <>
+__device__ __forceinline__ bool to_ll<double>(double v, long long& out) {
+    if (!(fabs(v) < 4.0e18) || v != rint(v)) return false;
+    out = (long long)v;
+    return true;
+}
+template <>
+__device__ __forceinline__ bool to_ll<float>(float v, long long& out) {
+    if (!(fabsf(v) < 4.0e18f) || v != rintf(v)) return false;
+    out = (long long)v;
+    return true;
+}
+
+__device__ __forceinline__ long long warp_min_ll(long long v) {
+    for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ long long warp_max_ll(long long v) {
+    for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+
+// exclusive block scan of one int per thread (RK_THREADS threads); returns the exclusive prefix,
+// *total receives the block total.  red: >= 33 ints of shared memory.
+__device__ __forceinline__ int block_excl_scan(int v, int* red, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) red[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0;
+        int winc = w;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        red[lane] = winc - w;
+        if (lane == 31) red[32] = winc;
+    }
+    __syncthreads();
+    int res = red[wid] + inc - v;
+    *total = red[32];
+    __syncthreads();
+    return res;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RK_THREADS, 1)
+rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t col0,
+                    const int32_t* __restrict__ slot_of_sample, uint16_t* __restrict__ ranks, int64_t rpad,
+                    int* max_distinct, int* flags, int32_t* fallback_list) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* bm = sm;                   // [BM_WORDS]
+    uint32_t* pre = sm + BM_WORDS;       // [BM_PRE]
+    int* red = (int*)(pre + BM_PRE);     // [40]
+    long long* redl = (long long*)(red + 40);  // [64]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t s = col0 + blockIdx.x;
+    const T* __restrict__ col = data + ld * s;
+
+    // phase 1: min / max / integrality
+    long long mn = LLONG_MAX, mx = LLONG_MIN;
+    int bad = 0;
+    for (int64_t g = tid; g < r; g += RK_THREADS) {
+        long long v;
+        if (!to_ll<T>(col[g], v)) bad = 1;
+        else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+    }
+    mn = warp_min_ll(mn); mx = warp_max_ll(mx);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) { redl[wid] = mn; redl[32 + wid] = mx; red[wid] = bad; }
+    __syncthreads();
+    if (wid == 0) {
+        mn = warp_min_ll(redl[lane]); mx = warp_max_ll(redl[32 + lane]);
+        bad = __any_sync(0xffffffffu, red[lane]);
+        if (lane == 0) { redl[0] = mn; redl[32] = mx; red[0] = bad; }
+    }
+    __syncthreads();
+    mn = redl[0]; mx = redl[32]; bad = red[0];
+    __syncthreads();
+    if (bad) {  // non-integral value: rank compression is not valid under the 0.1 tie band
+        if (tid == 0) atomicExch(&flags[0], 1);
+        return;
+    }
+    const unsigned long long range = (unsigned long long)mx - (unsigned long long)mn;
+    if (range >= (unsigned long long)BM_WORDS * 32ull) {
+        if (tid == 0) { int k = atomicAdd(&flags[1], 1); fallback_list[k] = (int32_t)s; }
+        return;
+    }
+    // phase 2: presence bitmap of (v - min)
+    const int nwords = (int)(range >> 5) + 1;
+    const int ngroups = (nwords + BM_GROUP - 1) / BM_GROUP;
+    for (int w = tid; w < ngroups * BM_GROUP; w += RK_THREADS) bm[w] = 0u;
+    __syncthreads();
+    for (int64_t g = tid; g < r; g += RK_THREADS) {
+        long long v; to_ll<T>(col[g], v);
+        const uint32_t k = (uint32_t)((unsigned long long)v - (unsigned long long)mn);
+        atomicOr(&bm[k >> 5], 1u << (k & 31));
+    }
+    __syncthreads();
+    // phase 3: exclusive prefix of popcounts per group of BM_GROUP words
+    int loc[BM_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int q = 0; q < BM_ITEMS; ++q) {
+        const int grp = tid * BM_ITEMS + q;
+        int cnt = 0;
+        if (grp < ngroups) {
+#pragma unroll
+            for (int w = 0; w < BM_GROUP; ++w) cnt += __popc(bm[grp * BM_GROUP + w]);
+        }
+        loc[q] = sum; sum += cnt;
+    }
+    int total;
+    const int base = block_excl_scan(sum, red, &total);
+#pragma unroll
+    for (int q = 0; q < BM_ITEMS; ++q) {
+        const int grp = tid * BM_ITEMS + q;
+        if (grp < ngroups) pre[grp] = (uint32_t)(base + loc[q]);
+    }
+    if (tid == 0) atomicMax(max_distinct, total);
+    __syncthreads();
+    // phase 4: dense rank lookup
+    const int64_t slot = slot_of_sample[s];
+    uint16_t* __restrict__ out = ranks + slot * rpad;
+    for (int64_t g = tid; g < r; g += RK_THREADS) {
+        long long v; to_ll<T>(col[g], v);
+        const uint32_t k = (uint32_t)((unsigned long long)v - (unsigned long long)mn);
+        const uint32_t wq = k >> 5;
+        uint32_t rk = pre[wq / BM_GROUP];
+        for (uint32_t w = (wq / BM_GROUP) * BM_GROUP; w < wq; ++w) rk += __popc(bm[w]);
+        rk += __popc(bm[wq] & ((1u << (k & 31)) - 1u));
+        out[g] = (uint16_t)rk;
+    }
+}
+
+// ---- fallback: sort-based dense rank in a global-memory scratch (rare: value range > bitmap) ----
+template <typename T>
+__global__ void __launch_bounds__(RK_THREADS, 1)
+rank_fallback_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* __restrict__ list,
+                     const int32_t* __restrict__ slot_of_sample, uint16_t* __restrict__ ranks, int64_t rpad,
+                     int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank, int64_t n) {
+    __shared__ int red[40];
+    const int tid = threadIdx.x;
+    const int64_t s = list[blockIdx.x];
+    const T* __restrict__ col = data + ld * s;
+    unsigned long long* keys = scratch_keys + (int64_t)blockIdx.x * n;
+    uint32_t* dr = scratch_rank + (int64_t)blockIdx.x * n;
+    for (int64_t g = tid; g < n; g += RK_THREADS) {
+        unsigned long long k = ~0ull;
+        if (g < r) { long long v; to_ll<T>(col[g], v); k = (unsigned long long)v ^ 0x8000000000000000ull; }
+        keys[g] = k;
+    }
+    __syncthreads();
+    for (int64_t k = 2; k <= n; k <<= 1) {
+        for (int64_t j = k >> 1; j > 0; j >>= 1) {
+            for (int64_t i = tid; i < n; i += RK_THREADS) {
+                const int64_t l = i ^ j;
+                if (l > i) {
+                    const bool asc = (i & k) == 0;
+                    const unsigned long long a = keys[i], b = keys[l];
+                    if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // dense rank of each sorted position: (number of distinct keys <= it) - 1
+    const int64_t per = (r + RK_THREADS - 1) / RK_THREADS;
+    const int64_t lo = (int64_t)tid * per, hi = (lo + per < r) ? lo + per : r;
+    int cnt = 0;
+    for (int64_t i = lo; i < hi; ++i) cnt += (i == 0 || keys[i] != keys[i - 1]);
+    int total;
+    int base = block_excl_scan(cnt, red, &total);
+    for (int64_t i = lo; i < hi; ++i) {
+        base += (i == 0 || keys[i] != keys[i - 1]);
+        dr[i] = (uint32_t)(base - 1);
+    }
+    if (tid == 0) atomicMax(max_distinct, total);
+    __syncthreads();
+    const int64_t slot = slot_of_sample[s];
+    uint16_t* __restrict__ out = ranks + slot * rpad;
+    for (int64_t g = tid; g < r; g += RK_THREADS) {
+        long long v; to_ll<T>(col[g], v);
+        const unsigned long long key = (unsigned long long)v ^ 0x8000000000000000ull;
+        int64_t a = 0, b = r;  // lower_bound
+        while (a < b) { const int64_t m = (a + b) >> 1; if (keys[m] < key) a = m + 1; else b = m; }
+        out[g] = (uint16_t)dr[a];
+    }
+}
+
+static size_t rank_smem_bytes() { return (size_t)(BM_WORDS + BM_PRE + 40) * 4 + 64 * 8 + 16; }
+
+cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
+                                    const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                    int* max_distinct, int* flags, int32_t* fallback_list, cudaStream_t st) {
+    const size_t smem = rank_smem_bytes();
+    cudaError_t e;
+#define LAUNCH_RK(T)                                                                                         \
+    e = cudaFuncSetAttribute(rank_columns_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                          \
+    rank_columns_kernel<T><<<ncols, RK_THREADS, smem, st>>>((const T*)data, r, ld, col0, slot_of_sample, ranks, \
+                                                            rpad, max_distinct, flags, fallback_list);
+    switch (dtype) {
+        case REO_I64: LAUNCH_RK(long long); break;
+        case REO_F64: LAUNCH_RK(double); break;
+        case REO_I32: LAUNCH_RK(int); break;
+        case REO_F32: LAUNCH_RK(float); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef LAUNCH_RK
+    return cudaGetLastError();
+}
+
+cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* fallback_list,
+                                     int nfb, const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                     int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank,
+                                     int64_t rpow2, cudaStream_t st) {
+#define LAUNCH_FB(T)                                                                                              \
+    rank_fallback_kernel<T><<<nfb, RK_THREADS, 0, st>>>((const T*)data, r, ld, fallback_list, slot_of_sample, ranks, \
+                                                        rpad, max_distinct, scratch_keys, scratch_rank, rpow2);
+    switch (dtype) {
+        case REO_I64: LAUNCH_FB(long long); break;
+        case REO_F64: LAUNCH_FB(double); break;
+        case REO_I32: LAUNCH_FB(int); break;
+        case REO_F32: LAUNCH_FB(float); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef LAUNCH_FB
+    return cudaGetLastError();
+}
+
+// ---- bit-plane transpose ------------------------------------------------------------------------
+// block (64, 4): thread (l, y) builds the NP words of gene t*64+l for sample word w = 4*blockIdx.y+y.
+__global__ void __launch_bounds__(256)
+bitplanes_kernel(const uint16_t* __restrict__ ranks, int64_t rpad, int64_t r,
+                 const int32_t* __restrict__ sample_of_slot, int W, int NP, uint32_t seed_lo, uint32_t seed_hi,
+                 uint32_t* __restrict__ planes) {
+    const int t = blockIdx.x, l = threadIdx.x;
+    const int w = blockIdx.y * 4 + threadIdx.y;
+    if (w >= W) return;
+    const int64_t g = (int64_t)t * REO_TILE + l;
+    uint32_t wd[REO_MAX_PLANES];
+#pragma unroll
+    for (int p = 0; p < REO_MAX_PLANES; ++p) wd[p] = 0u;
+    if (g < r) {
+#pragma unroll 4
+        for (int b = 0; b < 32; ++b) {
+            const int64_t S = (int64_t)w * 32 + b;
+            const int so = sample_of_slot[S];
+            if (so >= 0) {
+                const uint32_t rk = ranks[S * rpad + g];
+                wd[0] |= reo_coin_u(seed_lo, seed_hi, (uint32_t)g, (uint32_t)so) << b;
+#pragma unroll
+                for (int q = 0; q < REO_MAX_BITS; ++q) wd[q + 1] |= ((rk >> q) & 1u) << b;
+            }
+        }
+    }
+    uint32_t* out = planes + ((size_t)t * W + w) * NP * REO_TILE + l;
+#pragma unroll
+    for (int p = 0; p < REO_MAX_PLANES; ++p)
+        if (p < NP) out[(size_t)p * REO_TILE] = wd[p];
+}
+
+cudaError_t reo_launch_bitplanes(const uint16_t* ranks, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
+                                 int NT, int W, int NP, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes,
+                                 cudaStream_t st) {
+    dim3 grid(NT, (W + 3) / 4), block(REO_TILE, 4);
+    bitplanes_kernel<<<grid, block, 0, st>>>(ranks, rpad, r, sample_of_slot, W, NP, seed_lo, seed_hi, planes);
+    return cudaGetLastError();
+}
+
+// ---- column panel gather ------------------------------------------------------------------------
+// panel[tc][w][p][l] = planes[col_gene/64][w][p][col_gene%64]; pad columns (col_gene < 0) -> 0.
+__global__ void __launch_bounds__(256)
+gather_panel_kernel(const uint32_t* __restrict__ planes, int W, int NP, const int32_t* __restrict__ col_gene,
+                    uint32_t* __restrict__ panel) {
+    const int tc = blockIdx.x, l = threadIdx.x & 63;
+    const int g = col_gene[tc * REO_TILE + l];
+    const int total = W * NP;
+    for (int wp = blockIdx.y * 4 + (threadIdx.x >> 6); wp < total; wp += gridDim.y * 4) {
+        uint32_t v = 0u;
+        if (g >= 0) v = planes[((size_t)(g >> 6) * total + wp) * REO_TILE + (g & 63)];
+        panel[((size_t)tc * total + wp) * REO_TILE + l] = v;
+    }
+}
+
+cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const int32_t* col_gene, int ntc,
+                                    uint32_t* panel, cudaStream_t st) {
+    if (ntc <= 0) return cudaSuccess;
+    int gy = (W * NP + 3) / 4;
+    if (gy > 64) gy = 64;
+    dim3 grid(ntc, gy);
+    gather_panel_kernel<<<grid, 256, 0, st>>>(planes, W, NP, col_gene, panel);
+    return cudaGetLastError();
+}

@@ -1,0 +1,459 @@
+// reo_stats.cu -- K3..K6: per-gene McCullagh test, empirical null, Benjamini-Hochberg, reference-mask
+// update.  All FP64, on the device, compiled with -fmad=false so that the operation order below is
+// exactly the order of the restatement in oracle/reo_oracle.c (which follows Julia's LAPACK path
+// and reproduces the reference's known-answer vector bit for bit).
+//
+// Reference: src/RankCompV3.jl:225-259 (McCullagh_test), 409-417 (sort, trimmed std, p, BH, mask),
+// 426-429 (up/down).  These are O(r) latency-bound kernels (r <= 65535 genes).
+#include <math.h>
+
+#include "reo_internal.cuh"
+
+#define REO_INVSQRT2 0.7071067811865476
+#define MCC_MAXM 8  // tables up to 9 x 9
+
+// ------------------------------------------------------------------------------------------------
+// McCullagh_test, src:225-259, general k x k (k <= 9), LAPACK operation order (dgetf2 / dtrti2 /
+// dgetri unblocked, reciprocal pivot scaling, no FMA).  mat row-major.
+// ------------------------------------------------------------------------------------------------
+__device__ void mccullagh_device(const long long* mat, int k, double* out) {
+    const int m = k - 1;
+    long long N[MCC_MAXM][MCC_MAXM];
+    double A[MCC_MAXM][MCC_MAXM], nf[MCC_MAXM], Rf[MCC_MAXM], w2[MCC_MAXM], w1[MCC_MAXM], work[MCC_MAXM];
+    int piv[MCC_MAXM];
+    for (int i = 1; i < k; ++i)
+        for (int j = i; j < k; ++j) {
+            long long v = 0;
+            for (int a = 0; a < i; ++a) for (int b = j; b < k; ++b) v += mat[a * k + b];
+            for (int a = j; a < k; ++a) for (int b = 0; b < i; ++b) v += mat[a * k + b];
+            N[i - 1][j - 1] = v; N[j - 1][i - 1] = v;
+        }
+    for (int i = 1; i < k; ++i) {
+        long long v = 0;
+        for (int a = 0; a < i; ++a) for (int b = i; b < k; ++b) v += mat[a * k + b];
+        Rf[i - 1] = (double)v;
+    }
+    for (int i = 0; i < m; ++i) nf[i] = (double)N[i][i];
+    out[0] = 1.0; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0; out[4] = 0.0;
+    bool diag = true;
+    for (int i = 0; i < m; ++i) for (int j = i + 1; j < m; ++j) if (N[i][j] != 0) diag = false;
+    const double eps = 2.220446049250313e-16;
+    if (diag) {
+        for (int i = 0; i < m; ++i) if (N[i][i] == 0) return;
+        for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) A[i][j] = (i == j) ? 1.0 / nf[i] : 0.0;
+    } else {
+        double sign = 1.0;
+        for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) A[i][j] = (double)N[i][j];
+        for (int j = 0; j < m; ++j) {
+            int p = j; double best = fabs(A[j][j]);
+            for (int i = j + 1; i < m; ++i) if (fabs(A[i][j]) > best) { best = fabs(A[i][j]); p = i; }
+            piv[j] = p;
+            if (A[p][j] != 0.0) {
+                if (p != j) { for (int c = 0; c < m; ++c) { double t = A[j][c]; A[j][c] = A[p][c]; A[p][c] = t; } sign = -sign; }
+                const double rinv = 1.0 / A[j][j];
+                for (int i = j + 1; i < m; ++i) A[i][j] = A[i][j] * rinv;
+            }
+            for (int jj = j + 1; jj < m; ++jj)
+                for (int i = j + 1; i < m; ++i) A[i][jj] = A[i][jj] - A[i][j] * A[j][jj];
+        }
+        double det = sign;
+        for (int i = 0; i < m; ++i) det = det * A[i][i];
+        if (fabs(det) <= eps) return;
+        for (int j = 0; j < m; ++j) {
+            A[j][j] = 1.0 / A[j][j];
+            const double ajj = -A[j][j];
+            for (int jj = 0; jj < j; ++jj) {
+                if (A[jj][j] != 0.0) {
+                    const double temp = A[jj][j];
+                    for (int i = 0; i < jj; ++i) A[i][j] = A[i][j] + temp * A[i][jj];
+                    A[jj][j] = A[jj][j] * A[jj][jj];
+                }
+            }
+            for (int i = 0; i < j; ++i) A[i][j] = ajj * A[i][j];
+        }
+        for (int j = m - 2; j >= 0; --j) {
+            for (int i = j + 1; i < m; ++i) { work[i] = A[i][j]; A[i][j] = 0.0; }
+            for (int kk = j + 1; kk < m; ++kk) {
+                const double temp = -work[kk];
+                if (temp != 0.0) for (int i = 0; i < m; ++i) A[i][j] = A[i][j] + temp * A[i][kk];
+            }
+        }
+        for (int j = m - 2; j >= 0; --j) {
+            const int jp = piv[j];
+            if (jp != j) for (int i = 0; i < m; ++i) { double t = A[i][j]; A[i][j] = A[i][jp]; A[i][jp] = t; }
+        }
+    }
+    for (int i = 0; i < m; ++i) w2[i] = 0.0;
+    for (int kk = 0; kk < m; ++kk) for (int i = 0; i < m; ++i) w2[i] = w2[i] + nf[kk] * A[i][kk];
+    double s = 0.0;
+    for (int i = 0; i < m; ++i) s = s + nf[i] * w2[i];
+    const double nu = 1.0 / s;
+    for (int i = 0; i < m; ++i) w1[i] = (nf[i] * w2[i]) * nu;
+    double d1 = 0.0, sa = 0.0, sb = 0.0;
+    for (int i = 0; i < m; ++i) d1 = d1 + w1[i] * log((Rf[i] + 0.5) / ((nf[i] - Rf[i]) + 0.5));
+    for (int i = 0; i < m; ++i) { sa = sa + w2[i] * Rf[i]; sb = sb + w2[i] * (nf[i] - Rf[i]); }
+    const double d2 = log((0.5 + sa) / (0.5 + sb));
+    const double v1 = 4 * (1 + 0.25 * (d1 * d1)) * nu;
+    const double v2 = 4 * (1 + 0.25 * (d2 * d2)) * nu;
+    const double se = sqrt((v1 + v2) * 0.5);
+    const double z1 = d1 / se;
+    const double cdf = erfc(-z1 * REO_INVSQRT2) / 2, ccdf = erfc(z1 * REO_INVSQRT2) / 2;
+    const double p = 2 * (cdf < ccdf ? cdf : ccdf);
+    out[0] = p < 1.0 ? p : 1.0; out[1] = d1; out[2] = d2; out[3] = se; out[4] = z1;
+}
+
+// per gene: 3x3 table -> result columns 2..14 (col-major r x 15); src:403-405
+__global__ void mccullagh_tables_kernel(const int32_t* __restrict__ table, int64_t r, double* __restrict__ result) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r) return;
+    long long mat[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) mat[q] = table[i * 9 + q];
+    double o[5];
+    mccullagh_device(mat, 3, o);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) result[i + r * (2 + q)] = (double)mat[q];
+    result[i + r * 11] = o[1]; result[i + r * 12] = o[2]; result[i + r * 13] = o[3]; result[i + r * 14] = o[4];
+}
+cudaError_t reo_launch_mccullagh_tables(const int32_t* table, int64_t r, double* result, cudaStream_t st) {
+    mccullagh_tables_kernel<<<(unsigned)((r + 127) / 128), 128, 0, st>>>(table, r, result);
+    return cudaGetLastError();
+}
+
+__global__ void mccullagh_kxk_kernel(const long long* __restrict__ tables, int64_t n, int k, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long mat[81];
+    for (int q = 0; q < k * k; ++q) mat[q] = tables[i * k * k + q];
+    double o[5];
+    mccullagh_device(mat, k, o);
+    for (int q = 0; q < 5; ++q) out[i * 5 + q] = o[q];
+}
+cudaError_t reo_launch_mccullagh_kxk(const int64_t* tables, int64_t n, int k, double* out, cudaStream_t st) {
+    if (k < 2 || k > MCC_MAXM + 1) return cudaErrorInvalidValue;
+    mccullagh_kxk_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>((const long long*)tables, n, k, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable ascending sort of doubles: chunk bitonic sort in shared memory + cross-chunk ranking.
+// Total order = (Julia isless key, original index): -0.0 < 0.0, NaN last.
+// ------------------------------------------------------------------------------------------------
+#define SORT_CHUNK 2048
+#define SORT_THREADS 1024
+
+__device__ __forceinline__ unsigned long long f64_key(double x) {
+    if (x != x) return ~0ull;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ bool kv_less(unsigned long long ka, uint32_t ia, unsigned long long kb, uint32_t ib) {
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_chunks_kernel(const double* __restrict__ x, int64_t n, unsigned long long* __restrict__ keys,
+                   uint32_t* __restrict__ idx) {
+    __shared__ unsigned long long sk[SORT_CHUNK];
+    __shared__ uint32_t si[SORT_CHUNK];
+    const int64_t base = (int64_t)blockIdx.x * SORT_CHUNK;
+    for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) {
+        const int64_t g = base + i;
+        sk[i] = g < n ? f64_key(x[g]) : ~0ull;
+        si[i] = g < n ? (uint32_t)g : 0xffffffffu;
+    }
+    __syncthreads();
+    for (int k = 2; k <= SORT_CHUNK; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool asc = (i & k) == 0;
+                    const unsigned long long a = sk[i], b = sk[l];
+                    const uint32_t ia = si[i], ib = si[l];
+                    const bool gt = kv_less(b, ib, a, ia);
+                    if (gt == asc) { sk[i] = b; sk[l] = a; si[i] = ib; si[l] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) { keys[base + i] = sk[i]; idx[base + i] = si[i]; }
+}
+
+__global__ void sort_rank_kernel(const double* __restrict__ x, int64_t n, int nchunks,
+                                 const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx,
+                                 double* __restrict__ sorted, int32_t* __restrict__ perm) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)nchunks * SORT_CHUNK) return;
+    const uint32_t ie = idx[e];
+    if (ie == 0xffffffffu) return;
+    const unsigned long long ke = keys[e];
+    const int mych = (int)(e / SORT_CHUNK);
+    int64_t pos = e - (int64_t)mych * SORT_CHUNK;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch == mych) continue;
+        const unsigned long long* ck = keys + (int64_t)ch * SORT_CHUNK;
+        const uint32_t* ci = idx + (int64_t)ch * SORT_CHUNK;
+        int a = 0, b = SORT_CHUNK;  // number of elements of chunk ch that are < (ke, ie)
+        while (a < b) { const int m = (a + b) >> 1; if (kv_less(ck[m], ci[m], ke, ie)) a = m + 1; else b = m; }
+        pos += a;
+    }
+    sorted[pos] = x[ie];
+    if (perm) perm[pos] = (int32_t)ie;
+}
+
+cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,
+                                cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int nchunks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
+    const int64_t need = (int64_t)nchunks * SORT_CHUNK;
+    if (ws.cap < need) {
+        if (ws.keys) cudaFree(ws.keys);
+        if (ws.idx) cudaFree(ws.idx);
+        ws.keys = nullptr; ws.idx = nullptr; ws.cap = 0;
+        cudaError_t e = cudaMalloc(&ws.keys, need * sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&ws.idx, need * sizeof(uint32_t));
+        if (e != cudaSuccess) return e;
+        ws.cap = need;
+    }
+    sort_chunks_kernel<<<nchunks, SORT_THREADS, 0, st>>>(x, n, ws.keys, ws.idx);
+    sort_rank_kernel<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(x, n, nchunks, ws.keys, ws.idx, sorted, perm);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// trimmed std, src:411: std(sorted[lo:hi]) with Julia's pairwise reduction tree (block 1024,
+// sequential base case), two-pass, n-1 denominator.  One CTA; leaves are summed in parallel and
+// combined in the exact tree order by one thread.
+// ------------------------------------------------------------------------------------------------
+#define STD_MAX_LEAVES 256
+#define STD_THREADS 256
+
+__device__ double std_combine(int64_t lo, int64_t hi, const double* leaf, int* next) {
+    if (lo == hi || hi - lo < 1024) return leaf[(*next)++];
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    const double v1 = std_combine(lo, mid, leaf, next);
+    const double v2 = std_combine(mid + 1, hi, leaf, next);
+    return v1 + v2;
+}
+
+__global__ void __launch_bounds__(STD_THREADS)
+trimmed_std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ se_out) {
+    __shared__ int64_t llo[STD_MAX_LEAVES], lhi[STD_MAX_LEAVES];
+    __shared__ double lsum[STD_MAX_LEAVES];
+    __shared__ int nleaf;
+    __shared__ double mean_s;
+    if (threadIdx.x == 0) {
+        int64_t slo[64], shi[64];
+        int sp = 0, nl = 0;
+        slo[0] = lo0; shi[0] = hi0; sp = 1;
+        while (sp > 0) {
+            --sp;
+            const int64_t lo = slo[sp], hi = shi[sp];
+            if (lo == hi || hi - lo < 1024) { llo[nl] = lo; lhi[nl] = hi; ++nl; }
+            else {
+                const int64_t mid = lo + ((hi - lo) >> 1);
+                slo[sp] = mid + 1; shi[sp] = hi; ++sp;   // right is popped after left
+                slo[sp] = lo; shi[sp] = mid; ++sp;
+            }
+        }
+        nleaf = nl;
+    }
+    __syncthreads();
+    const int64_t m = hi0 - lo0 + 1;
+    for (int pass = 0; pass < 2; ++pass) {
+        const double mean = pass ? mean_s : 0.0;
+        for (int l = threadIdx.x; l < nleaf; l += STD_THREADS) {
+            const int64_t lo = llo[l], hi = lhi[l];
+            double v;
+            if (pass == 0) {
+                if (lo == hi) v = sorted[lo];
+                else { v = sorted[lo] + sorted[lo + 1]; for (int64_t i = lo + 2; i <= hi; ++i) v = v + sorted[i]; }
+            } else {
+                if (lo == hi) v = (sorted[lo] - mean) * (sorted[lo] - mean);
+                else {
+                    v = (sorted[lo] - mean) * (sorted[lo] - mean) + (sorted[lo + 1] - mean) * (sorted[lo + 1] - mean);
+                    for (int64_t i = lo + 2; i <= hi; ++i) v = v + (sorted[i] - mean) * (sorted[i] - mean);
+                }
+            }
+            lsum[l] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int next = 0;
+            const double tot = std_combine(lo0, hi0, lsum, &next);
+            if (pass == 0) mean_s = tot / (double)m;
+            else *se_out = sqrt(tot / (double)(m - 1));
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* /*leaf_ws*/,
+                                   cudaStream_t st) {
+    // round(Int, r*0.05) : round(Int, r*0.95), 1-based inclusive, round-half-even on the FP64 product
+    const int64_t lo = (int64_t)nearbyint((double)n * 0.05), hi = (int64_t)nearbyint((double)n * 0.95);
+    if (lo < 1 || hi > n || hi < lo) return cudaErrorInvalidValue;
+    if ((hi - lo + 1) / 512 + 2 > STD_MAX_LEAVES) return cudaErrorInvalidValue;
+    trimmed_std_kernel<<<1, STD_THREADS, 0, st>>>(sorted, lo - 1, hi - 1, se_out);
+    return cudaGetLastError();
+}
+
+// src:412: pvalue(Normal(0, se), d1; tail = :both) -> result column 0
+__global__ void null_pvals_kernel(const double* __restrict__ d1, int64_t n, const double* __restrict__ se_p,
+                                  double* __restrict__ pval) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double se = *se_p, d = d1[i];
+    double z;
+    if (se == 0.0) z = (d == 0.0) ? 0.0 : copysign(INFINITY, d);
+    else z = (d - 0.0) / se;
+    const double cdf = erfc(-z * REO_INVSQRT2) / 2, ccdf = erfc(z * REO_INVSQRT2) / 2;
+    const double p = 2 * (cdf < ccdf ? cdf : ccdf);
+    pval[i] = p < 1.0 ? p : 1.0;
+}
+cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se, double* pval, cudaStream_t st) {
+    null_pvals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d1, n, se, pval);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Benjamini-Hochberg, src:413 (MultipleTesting 0.5.1): q_(m) = p_(m) * (n/m), reverse running
+// minimum, min(.,1), un-permute.  One CTA; suffix-min by per-thread chunks + block scan.
+// ------------------------------------------------------------------------------------------------
+#define BH_THREADS 1024
+__global__ void __launch_bounds__(BH_THREADS)
+bh_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64_t n, double* __restrict__ padj) {
+    __shared__ double cmin[BH_THREADS];
+    const int tid = threadIdx.x;
+    const int64_t per = (n + BH_THREADS - 1) / BH_THREADS;
+    const int64_t lo = (int64_t)tid * per, hi = (lo + per < n) ? lo + per : n;
+    double mn = INFINITY;
+    for (int64_t i = hi - 1; i >= lo; --i) {
+        const double q = sp[i] * ((double)n / (double)(i + 1));
+        mn = q < mn ? q : mn;
+    }
+    cmin[tid] = mn;
+    __syncthreads();
+    // suffix minimum over chunk minima (exclusive: chunks strictly to the right)
+    if (tid == 0) {
+        double run = INFINITY;
+        for (int t = BH_THREADS - 1; t >= 0; --t) { const double v = cmin[t]; cmin[t] = run; run = v < run ? v : run; }
+    }
+    __syncthreads();
+    double run = cmin[tid];
+    for (int64_t i = hi - 1; i >= lo; --i) {
+        const double q = sp[i] * ((double)n / (double)(i + 1));
+        run = q < run ? q : run;
+        padj[perm[i]] = run < 1.0 ? run : 1.0;
+    }
+}
+cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* /*ws*/,
+                          cudaStream_t st) {
+    bh_kernel<<<1, BH_THREADS, 0, st>>>(sorted_p, perm, n, padj);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask update, src:417-424, and ordered compaction of masks into column lists
+// ------------------------------------------------------------------------------------------------
+#define MK_THREADS 1024
+__device__ __forceinline__ int mk_block_scan(int v, int* red, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) red[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = red[lane];
+        int winc = w;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        red[lane] = winc - w;
+        if (lane == 31) red[32] = winc;
+    }
+    __syncthreads();
+    const int res = red[wid] + inc - v;
+    *total = red[32];
+    __syncthreads();
+    return res;
+}
+
+// inds = .!((pval .<= pval_deg) .&& (padj .<= padj_deg)), src:417
+__global__ void inds_kernel(const double* __restrict__ pval, const double* __restrict__ padj, int64_t r,
+                            double pval_deg, double padj_deg, uint8_t* __restrict__ mask_new) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r) return;
+    mask_new[i] = !((pval[i] <= pval_deg) && (padj[i] <= padj_deg));
+}
+
+// counts[0] = sum(old), counts[1] = sum(new), counts[2] = |old xor new|; ascending signed list of changes
+__global__ void __launch_bounds__(MK_THREADS)
+mask_diff_kernel(int64_t r, const uint8_t* __restrict__ mask_old, const uint8_t* __restrict__ mask_new,
+                 int32_t* __restrict__ counts, int32_t* __restrict__ changed_gene, int8_t* __restrict__ changed_sign) {
+    __shared__ int red[40];
+    const int tid = threadIdx.x;
+    const int64_t per = (r + MK_THREADS - 1) / MK_THREADS;
+    const int64_t lo = (int64_t)tid * per, hi = (lo + per < r) ? lo + per : r;
+    int n_old = 0, n_new = 0, n_chg = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint8_t nd = mask_new[i] != 0, od = mask_old[i] != 0;
+        n_old += od; n_new += nd; n_chg += (od != nd);
+    }
+    int t_old, t_new, t_chg;
+    mk_block_scan(n_old, red, &t_old);
+    mk_block_scan(n_new, red, &t_new);
+    int pos = mk_block_scan(n_chg, red, &t_chg);
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint8_t nd = mask_new[i] != 0, od = mask_old[i] != 0;
+        if (od != nd) { changed_gene[pos] = (int32_t)i; changed_sign[pos] = nd ? 1 : -1; ++pos; }
+    }
+    const int padded = (t_chg + REO_TILE - 1) / REO_TILE * REO_TILE;
+    for (int i = t_chg + tid; i < padded; i += MK_THREADS) { changed_gene[i] = -1; changed_sign[i] = 0; }
+    if (tid == 0) { counts[0] = t_old; counts[1] = t_new; counts[2] = t_chg; }
+}
+cudaError_t reo_launch_inds(const double* pval, const double* padj, int64_t r, double pval_deg, double padj_deg,
+                            uint8_t* mask_new, cudaStream_t st) {
+    inds_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(pval, padj, r, pval_deg, padj_deg, mask_new);
+    return cudaGetLastError();
+}
+cudaError_t reo_launch_mask_diff(int64_t r, const uint8_t* mask_old, const uint8_t* mask_new, int32_t* counts,
+                                 int32_t* changed_gene, int8_t* changed_sign, cudaStream_t st) {
+    mask_diff_kernel<<<1, MK_THREADS, 0, st>>>(r, mask_old, mask_new, counts, changed_gene, changed_sign);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(MK_THREADS)
+mask_to_list_kernel(const uint8_t* __restrict__ mask, int64_t r, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    __shared__ int red[40];
+    const int tid = threadIdx.x;
+    const int64_t per = (r + MK_THREADS - 1) / MK_THREADS;
+    const int64_t lo = (int64_t)tid * per, hi = (lo + per < r) ? lo + per : r;
+    int n = 0;
+    for (int64_t i = lo; i < hi; ++i) n += mask[i] != 0;
+    int total;
+    int pos = mk_block_scan(n, red, &total);
+    for (int64_t i = lo; i < hi; ++i) if (mask[i]) list[pos++] = (int32_t)i;
+    const int padded = (total + REO_TILE - 1) / REO_TILE * REO_TILE;
+    for (int i = total + tid; i < padded; i += MK_THREADS) list[i] = -1;
+    if (tid == 0) *count = total;
+}
+cudaError_t reo_launch_mask_to_list(const uint8_t* mask, int64_t r, int32_t* list, int32_t* count, cudaStream_t st) {
+    mask_to_list_kernel<<<1, MK_THREADS, 0, st>>>(mask, r, list, count);
+    return cudaGetLastError();
+}
+
+// src:426-429
+__global__ void updown_kernel(const double* __restrict__ result, int64_t r, double pval_deg, double padj_deg,
+                              int8_t* __restrict__ updown) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r) return;
+    const bool sig = (result[i] <= pval_deg) && (result[i + r] <= padj_deg);
+    const double z = result[i + r * 14];
+    updown[i] = (int8_t)((sig && z > 0) ? 1 : ((sig && z < 0) ? -1 : 0));
+}
+cudaError_t reo_launch_updown(const double* result, int64_t r, double pval_deg, double padj_deg, int8_t* updown,
+                              cudaStream_t st) {
+    updown_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(result, r, pval_deg, padj_deg, updown);
+    return cudaGetLastError();
+}

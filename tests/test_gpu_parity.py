@@ -1,0 +1,265 @@
+"""GPU suite (-m gpu): parity of the CUDA path, called through the C ABI, against the CPU oracle.
+Bars: pair counts, classes and contingency tables bit-exact; p-values and statistics within 1e-12 relative;
+identical up/down/no-change calls and iteration counts."""
+import json
+import os
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, small_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    e[(a == b)] = 0.0
+    return float(np.nanmax(e)) if e.size else 0.0
+
+
+# ---- K1 + pair counts -------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,r,n1,n2,n3,scale", [
+    (1, 70, 5, 5, 0, 4), (2, 200, 33, 31, 0, 8), (3, 130, 64, 1, 0, 2), (4, 90, 7, 40, 9, 8), (5, 65, 100, 100, 0, 16)])
+def test_pair_counts_bit_exact(reo, oracle, seed, r, n1, n2, n3, scale):
+    data, group = small_case(seed, r, n1, n2, scale=scale, n3=n3)
+    levels, gid = oracle.group_levels(group)
+    gnum = len(levels)
+    info = reo.stage(data, gid, gnum)
+    assert info["gene_tiles"] == -(-r // 64)
+    rng = np.random.default_rng(seed)
+    rows = rng.choice(r, min(r, 40), replace=False)
+    cols = rng.choice(r, min(r, 50), replace=False)
+    want = oracle.greater_counts(data, gid, gnum, rows, cols, seed=7)
+    for k in range(gnum if gnum > 2 else 1):
+        nre, rest = reo.pair_counts(k, rows, cols)
+        assert np.array_equal(nre, want[k])
+        assert np.array_equal(rest, want.sum(axis=0) - want[k])
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.float64, np.int32, np.float32])
+def test_dtypes_and_leading_dimension(reo, pkg, oracle, dtype):
+    data, group = small_case(9, 100, 10, 12)
+    levels, gid = oracle.group_levels(group)
+    rows = np.arange(0, 100, 3)
+    want = oracle.greater_counts(data, gid, 2, rows, rows, seed=7)
+    reo.stage(data.astype(dtype), gid, 2)
+    nre, rest = reo.pair_counts(0, rows, rows)
+    assert np.array_equal(nre, want[0]) and np.array_equal(rest, want[1])
+
+
+def test_wide_value_range_uses_sort_fallback(reo, oracle):
+    """Columns whose value range exceeds the shared-memory bitmap go through the sort-based rank kernel."""
+    data, group = small_case(12, 300, 9, 8)
+    data = data.astype(np.int64)
+    data[::7, :] *= 3_000_000          # range > 1.3 M in every column
+    data[5, 3] = -(2 ** 40)
+    levels, gid = oracle.group_levels(group)
+    reo.stage(data, gid, 2)
+    rows = np.arange(0, 300, 5)
+    want = oracle.greater_counts(data, gid, 2, rows, rows, seed=7)
+    nre, rest = reo.pair_counts(0, rows, rows)
+    assert np.array_equal(nre, want[0]) and np.array_equal(rest, want[1])
+
+
+def test_non_integral_input_is_refused_loudly(reo, oracle):
+    data, group = small_case(13, 50, 6, 6)
+    levels, gid = oracle.group_levels(group)
+    with pytest.raises(NotImplementedError):
+        reo.stage(data.astype(np.float64) + 0.05, gid, 2)
+
+
+# ---- K2 tables ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,r,n1,n2,frac", [(1, 70, 5, 5, 0.3), (2, 333, 33, 31, 0.2), (3, 200, 70, 3, 1.0),
+                                               (4, 129, 20, 45, 0.02), (6, 1000, 12, 12, 0.5)])
+def test_tables_bit_exact_and_delta(reo, oracle, coracle, seed, r, n1, n2, frac):
+    data, group = small_case(seed, r, n1, n2)
+    levels, gid = oracle.group_levels(group)
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    rng = np.random.default_rng(seed)
+    mask = rng.random(r) < frac
+    if frac >= 1.0:
+        mask[:] = True
+    reo.stage(data, gid, 2)
+    got = reo.tables(0, mask, thresholds=thr)
+    want, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got.sum(axis=1), mask.sum() - mask.astype(int))  # gene i never counts itself
+    # thresholds computed by the library from pval_reo
+    assert np.array_equal(reo.tables(0, mask, pval_reo=0.01), want)
+    # incremental path: build for `mask`, signed update over the symmetric difference to `mask2`
+    mask2 = mask.copy()
+    flip = rng.choice(r, max(r // 20, 1), replace=False)
+    mask2[flip] = ~mask2[flip]
+    want2, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask2)[0], seed=7)
+    assert np.array_equal(reo.tables(0, mask, thresholds=thr, mask_to=mask2), want2)
+
+
+def test_tables_three_groups_one_vs_rest(reo, oracle, coracle):
+    data, group = small_case(21, 150, 9, 40, n3=33)
+    levels, gid = oracle.group_levels(group)
+    thr = coracle.thresholds_for(gid, 3, 0.01)
+    mask = np.random.default_rng(0).random(150) < 0.4
+    reo.stage(data, gid, 3)
+    for k in range(3):
+        want, _ = coracle.block_tables(data, gid, 3, thr, np.nonzero(mask)[0], seed=7, k=k)
+        assert np.array_equal(reo.tables(k, mask, thresholds=thr), want), k
+
+
+def test_tables_mirror_property_all_genes(reo, oracle, coracle):
+    """With every gene a reference, each unordered pair contributes q to one gene and 10-q to the other
+    (src:385-386), so the column sums of the table are palindromic."""
+    data, group = small_case(8, 500, 40, 50)
+    levels, gid = oracle.group_levels(group)
+    reo.stage(data, gid, 2)
+    tab = reo.tables(0, np.ones(500, bool))
+    s = tab.sum(axis=0)
+    assert np.array_equal(s, s[::-1]) and tab.sum() == 500 * 499
+
+
+# ---- K3..K6 ----------------------------------------------------------------------------------------
+def test_mccullagh_kat_on_device(reo, pkg):
+    kat = json.load(open(os.path.join(GOLDEN, "kat_mccullagh.json")))
+    got = pkg.McCullagh_test(np.array(kat["mat"]), handle=reo)
+    # sqrt/div/mul/add are IEEE on the device; log and erfc may differ from libm in the last ulp
+    assert rel_err(got, kat["expected"]) <= RTOL
+    with pytest.raises(ValueError, match="square"):
+        pkg.McCullagh_test(np.zeros((3, 4), dtype=int), handle=reo)
+
+
+def test_mccullagh_random_tables(reo, coracle):
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 3000, size=(2000, 3, 3))
+    t[:50, 0, 1] = t[:50, 1, 0] = t[:50, 1, 2] = t[:50, 2, 1] = 0  # a = b = c: singular in exact arithmetic
+    t[50:60] = 0
+    got = reo.mccullagh(t)
+    want = np.array([coracle.mccullagh(x) for x in t])
+    assert rel_err(got[:, 1:], want[:, 1:]) <= RTOL
+    assert rel_err(got[:, 0], want[:, 0]) <= 1e-11  # the test's own p (overwritten in the pipeline, src:415)
+
+
+@pytest.mark.parametrize("n", [11, 30, 2047, 2049, 19999, 40000])
+def test_sort_empirical_null_bh(reo, oracle, coracle, n):
+    rng = np.random.default_rng(n)
+    d = rng.normal(0, 1.5, n)
+    d[rng.integers(0, n, n // 7)] = 0.0
+    d[rng.integers(0, n, 3)] = -0.0
+    s, perm = reo.sort(d)
+    assert np.array_equal(s, np.sort(d)) and np.array_equal(d[perm], s)
+    assert np.all((np.diff(s) > 0) | (np.diff(perm) > 0) | (np.signbit(s[:-1]) & ~np.signbit(s[1:])))  # stable
+    se_w, p_w = coracle.empirical_null(d)
+    se_g, p_g = reo.empirical_null(d)
+    assert se_g == se_w, (se_g, se_w)  # same reduction tree, IEEE ops: bit-exact
+    assert rel_err(p_g, p_w) <= RTOL
+    q_g = reo.bh(p_w)
+    assert np.array_equal(q_g, coracle.bh(p_w))
+
+
+def test_small_r_bounds_error(reo):
+    with pytest.raises(IndexError):
+        reo.empirical_null(np.zeros(10))
+
+
+# ---- the whole path -------------------------------------------------------------------------------
+def check_full(out, want):
+    assert out.iters == want["iters"]
+    assert np.array_equal(out.result[:, :, 2:11], want["result"][:, :, 2:11]), "contingency tables"
+    assert np.array_equal(out.updown, want["updown"]), "up/down/no-change calls"
+    assert np.array_equal(out.final_ref, want["final_ref"])
+    assert rel_err(out.result[:, :, 0], want["result"][:, :, 0]) <= RTOL  # pval
+    assert rel_err(out.result[:, :, 1], want["result"][:, :, 1]) <= RTOL  # padj
+    assert rel_err(out.result[:, :, 11:15], want["result"][:, :, 11:15]) <= RTOL
+
+
+@pytest.mark.parametrize("seed,r,n1,n2,n3,nref", [(1, 150, 7, 9, 0, 40), (2, 600, 33, 40, 0, 100),
+                                                  (3, 300, 6, 5, 7, 80), (4, 1200, 20, 20, 0, 300)])
+def test_identify_degs_matches_oracle(reo, oracle, coracle, seed, r, n1, n2, n3, nref):
+    data, group = small_case(seed, r, n1, n2, n3=n3)
+    levels, gid = oracle.group_levels(group)
+    gnum = len(levels)
+    ref = np.zeros(r, bool)
+    ref[np.random.default_rng(seed).choice(r, nref, replace=False)] = True
+    thr = coracle.thresholds_for(gid, gnum, 0.01)
+    want = coracle.identify_degs(data, gid, gnum, thr, 1.0, 0.05, ref, 128, 5, seed=7)
+    out = reo.identify_degs(data, gid, gnum, ref, 0.01, 1.0, 0.05, 128, 5)
+    check_full(out, want)
+    assert out.stats["n_deg"] == [int(v) for v in want["deg_log"][-1 if gnum > 2 else 0][:out.iters[-1]]]
+    # n_iter cap and explicit thresholds
+    want2 = coracle.identify_degs(data, gid, gnum, thr, 0.5, 0.1, ref, 2, 0, seed=7)
+    out2 = reo.identify_degs(data, gid, gnum, ref, 0.01, 0.5, 0.1, 2, 0, thresholds=thr)
+    check_full(out2, want2)
+
+
+def test_identify_degs_reference_signature(reo, pkg, oracle, coracle):
+    """The reference-named wrapper returns the r x (1+16K) matrix of src:430/437."""
+    data, group = small_case(5, 120, 8, 8)
+    names = [f"g{i}" for i in range(120)]
+    ref = np.arange(120) % 3 == 0
+    res = pkg.identify_degs(data, group, names, 0.01, 1.0, 0.05, ref, 128, 5, handle=reo)
+    assert res.shape == (120, 17) and list(res[:, 0]) == names
+    assert set(res[:, 16]) <= {"up", "down", "no change"}
+    levels, gid = oracle.group_levels(group)
+    want = coracle.identify_degs(data, gid, 2, coracle.thresholds_for(gid, 2, 0.01), 1.0, 0.05, ref, 128, 5, seed=7)
+    assert np.array_equal(res[:, 3:12].astype(np.int64), want["result"][0][:, 2:11].astype(np.int64))
+
+
+def test_golden_small_case_gpu(reo):
+    g = np.load(os.path.join(GOLDEN, "small_case.npz"))
+    out = reo.identify_degs(g["data"], g["gid"], 2, g["ref"], 0.01, 1.0, 0.05, 128, 5)
+    check_full(out, dict(result=g["result"], updown=g["updown"], final_ref=g["final_ref"], iters=g["iters"].tolist()))
+
+
+def test_golden_bundled_data_gpu(reo):
+    """Config 1: the reference's bundled test data (19999 x (5+5)), seeded 3000-gene reference mask."""
+    g = np.load(os.path.join(GOLDEN, "bundled_c1.npz"))
+    out = reo.identify_degs(g["data"], g["gid"], 2, g["ref"], 0.01, 1.0, 0.05, 128, 5)
+    assert out.iters == g["iters"].tolist()
+    assert np.array_equal(out.result[0][:, 2:11].astype(np.int32), g["tables"])
+    assert np.array_equal(out.updown[0], g["updown"]) and np.array_equal(out.final_ref[0], g["final_ref"])
+    assert rel_err(out.result[0][:, 0], g["pval"]) <= RTOL and rel_err(out.result[0][:, 1], g["padj"]) <= RTOL
+    assert rel_err(out.result[0][:, 11:15], g["stat"]) <= RTOL
+
+
+def test_tie_free_input_is_seed_independent(pkg, oracle, coracle):
+    """On tie-free data no coin is consulted: any seed gives the same result (= the real reference's)."""
+    data, group, is_de = pkg.synth.bulk(400, 12, 14, seed=2)
+    tf = pkg.synth.tie_free(data)
+    levels, gid = oracle.group_levels(group)
+    ref = pkg.synth.reference_mask(is_de, 80)
+    outs = []
+    for seed in (1, 99):
+        with pkg.Reo(0, seed=seed) as h:
+            outs.append(h.identify_degs(tf, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5))
+    assert np.array_equal(outs[0].result, outs[1].result)
+    want = coracle.identify_degs(tf, gid, 2, coracle.thresholds_for(gid, 2, 0.01), 1.0, 0.05, ref, 128, 5, seed=12345)
+    check_full(outs[0], want)
+
+
+def test_full_size_properties_config2(reo, pkg, oracle, coracle):
+    """BASELINE config 2 at full size (20k genes x 100 vs 100): size-independent properties + a sampled
+    row block against the oracle."""
+    data, group, is_de = pkg.synth.bulk(20000, 100, 100)
+    levels, gid = oracle.group_levels(group)
+    ref = pkg.synth.reference_mask(is_de, 3000)
+    out = reo.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5)
+    tab = out.result[0][:, 2:11].astype(np.int64)
+    fr = out.final_ref[0].astype(bool)
+    assert np.array_equal(tab.sum(axis=1), fr.sum() - fr.astype(int))
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    cols = np.nonzero(fr)[0]
+    want, _ = coracle.block_tables(data, gid, 2, thr, cols, seed=7, i0=4000, i1=4032)
+    assert np.array_equal(tab[4000:4032], want)
+    # statistics recomputed by the oracle from the device tables
+    res = out.result[0]
+    se_w, p_w = coracle.empirical_null(res[:, 11])
+    assert rel_err(res[:, 0], p_w) <= RTOL and rel_err(res[:, 1], coracle.bh(p_w)) <= RTOL
+    sig = (res[:, 0] <= 1.0) & (res[:, 1] <= 0.05)
+    assert np.array_equal(out.updown[0], np.where(sig & (res[:, 14] > 0), 1, np.where(sig & (res[:, 14] < 0), -1, 0)))
+    # the planted DE genes are recovered
+    called = out.updown[0] != 0
+    assert (called & is_de).sum() > 0.7 * is_de.sum() and (called & ~is_de).sum() < 0.1 * called.sum() + 50
+    assert out.stats["kernel_launches"] > 0 and out.stats["compares"] > 0

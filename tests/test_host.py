@@ -1,0 +1,81 @@
+"""CPU suite: the C-ABI library loads and exports every symbol of include/reo.h; host-side logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg._lib.load()
+    header = open(os.path.join(ROOT, "include", "reo.h")).read()
+    declared = set(re.findall(r"\b(reo_[a-z0-9_]+)\s*\(", header)) - {"reo_allgather_fn"}
+    assert declared == set(pkg._lib.SYMBOLS), declared ^ set(pkg._lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.reo_version() == 100
+
+
+def test_no_gpu_fails_loudly(pkg):
+    """Without a CUDA device the product path must raise, not fall back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(Exception) as e:
+        pkg.Reo(0)
+    assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    pdir = os.path.join(ROOT, "rankcompv3.jl_b200")
+    for dp, _, files in os.walk(pdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import reo_oracle" not in src and "import c_oracle" not in src and "oracle/" not in src \
+                    or f in ("reo_stats.cu", "reo_internal.cuh"), f  # comments naming the oracle are allowed there
+
+
+def test_group_levels(pkg):
+    lv, gid = pkg.api.group_levels(["b", "a", "b", "c", "a"])
+    assert lv == ["b", "a", "c"] and gid.tolist() == [0, 1, 0, 2, 1]
+
+
+def test_dimension_errors_before_gpu(pkg):
+    data = np.zeros((20, 4), dtype=np.int64)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        pkg.identify_degs(data, ["a", "b", "a"], list("x" * 20), 0.01, 1.0, 0.05, np.ones(20, bool), 4, 1)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        pkg.identify_degs(data, ["a"] * 4, list("x" * 20), 0.01, 1.0, 0.05, np.ones(20, bool), 4, 1)
+
+
+def test_pseudobulk_group(pkg):
+    """src:56-67: chunks of ceil(c/n_pseudo) cells, row sums, every cell used exactly once."""
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 10, size=(30, 103))
+    pb = pkg.pseudobulk_group(x, 10, np.random.default_rng(1))
+    assert pb.shape == (30, 10)  # ceil(103/10) = 11 cells per profile -> 10 profiles
+    assert np.array_equal(pb.sum(axis=1), x.sum(axis=1))
+    pb2 = pkg.pseudobulk_group(x, 50, np.random.default_rng(1))
+    assert pb2.shape[1] == 35  # ceil(103/50) = 3 -> 35 profiles: fewer than n_pseudo
+
+
+def test_synth_shapes(pkg):
+    d, g, de = pkg.synth.bulk(300, 6, 7, seed=1)
+    assert d.shape == (300, 13) and d.dtype == np.int64 and len(g) == 13 and de.sum() == 30
+    tf = pkg.synth.tie_free(d)
+    assert all(len(set(tf[:, s])) == 300 for s in range(13))
+    m = pkg.synth.reference_mask(de, 50)
+    assert m.sum() == 50 and not (m & de).any()
+
+
+def test_shard_plan(pkg):
+    from importlib import import_module
+    dist = import_module(pkg.__name__ + ".dist")
+    for nt, world in ((469, 8), (5, 8), (313, 2), (1, 1)):
+        tpr, ranges = dist.shard_plan(nt, world)
+        assert tpr == -(-nt // world) and len(ranges) == world
+        covered = [t for (a, b) in ranges for t in range(a, b)]
+        assert covered == list(range(nt))

@@ -1,0 +1,168 @@
+"""CPU suite: pins the oracle (oracle/) against the reference's known-answer vector, exact arithmetic, scipy,
+the committed golden fixtures, and its two independent restatements against each other."""
+import json
+import math
+import os
+from fractions import Fraction
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, small_case
+
+
+def test_kat_mccullagh_numpy_and_c(oracle, coracle):
+    """src/RankCompV3.jl:206-222 -- the reference's only known-answer vector, bit-exact."""
+    kat = json.load(open(os.path.join(GOLDEN, "kat_mccullagh.json")))
+    N, n, R = oracle.mccullagh_NR(kat["mat"])
+    assert N.tolist() == kat["N"] and R.tolist() == kat["R"]
+    got = oracle.mccullagh_test(kat["mat"])
+    assert [float(v) for v in got] == kat["expected"]
+    got_c = coracle.mccullagh(kat["mat"])
+    assert [float(v) for v in got_c] == kat["expected"]
+    # paper's rounded values, src:222
+    assert round(got[1], 2) == 1.45 and round(got[2], 2) == 1.50 and abs(got[3] - 0.53) < 0.01
+
+
+def test_mccullagh_variants_agree(oracle, coracle):
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        t = rng.integers(0, 400, size=(3, 3))
+        a = oracle.mccullagh_test(t, "lapack")
+        b = oracle.mccullagh_test(t, "closed")
+        c = coracle.mccullagh(t)
+        assert [float(v) for v in a] == [float(v) for v in c]
+        for x, y in zip(a[1:], b[1:]):
+            assert abs(x - y) <= 1e-9 * max(1.0, abs(y))
+
+
+def test_mccullagh_singular(oracle, coracle):
+    # b = 0 and a = 0 -> diagonal N with a zero -> (1, 0, 0, 0, 0), src:242-243
+    t = np.array([[5, 0, 0], [0, 7, 2], [0, 1, 9]])
+    assert oracle.mccullagh_test(t) == (1.0, 0.0, 0.0, 0.0, 0.0)
+    assert coracle.mccullagh(t) == (1.0, 0.0, 0.0, 0.0, 0.0)
+    assert oracle.mccullagh_test(np.zeros((3, 3), dtype=int)) == (1.0, 0.0, 0.0, 0.0, 0.0)
+
+
+def _exact_threshold(n, alpha):
+    alpha = Fraction(alpha)
+    if not (min(Fraction(1), Fraction(2, 2 ** n)) < alpha):
+        return n
+    for x in range(0, n // 2 + 1):
+        lo = sum(math.comb(n, k) for k in range(0, x + 1))
+        hi = sum(math.comb(n, k) for k in range(x, n + 1))
+        p = min(Fraction(1), 2 * Fraction(min(lo, hi), 2 ** n))
+        if p > alpha:
+            return n - x + 1
+
+
+def test_thresholds_exact_and_survey_values(oracle, coracle, pkg):
+    """src:81-92.  Survey-derived values + brute-force exact binomial sums."""
+    survey = {5: 5, 6: 6, 7: 7, 8: 8, 9: 9, 10: 10, 20: 17, 50: 35, 100: 64, 200: 119, 1000: 542, 10000: 5130,
+              20000: 10183}
+    for n, want in survey.items():
+        assert oracle.major_reo_lower_count(n, 0.01) == want
+        assert coracle.threshold(n, 0.01) == want
+        assert pkg.get_major_reo_lower_count(n, 0.01) == want  # host arithmetic of libreo_cuda.so
+    for n in list(range(1, 70)) + [97, 128, 255, 300]:
+        for alpha in (0.01, 0.05, 0.001, 0.2):
+            e = _exact_threshold(n, alpha)
+            assert oracle.major_reo_lower_count(n, alpha) == e
+            assert coracle.threshold(n, alpha) == e
+            assert pkg.get_major_reo_lower_count(n, alpha) == e
+            assert e > n / 2  # "i>j stable" and "i<j stable" are exclusive
+
+
+def test_bh_against_scipy(oracle, coracle):
+    from scipy.stats import false_discovery_control
+    rng = np.random.default_rng(1)
+    for n in (2, 11, 500, 4097):
+        p = rng.random(n) ** 3
+        p[rng.integers(0, n, n // 5)] = p[0]  # ties
+        want = false_discovery_control(p, method="bh")
+        assert np.allclose(oracle.bh_adjust(p), want, rtol=1e-13, atol=0)
+        assert np.array_equal(oracle.bh_adjust(p), coracle.bh(p))
+
+
+def test_empirical_null_two_restatements(oracle, coracle):
+    rng = np.random.default_rng(2)
+    for n in (11, 30, 1000, 5000):
+        d = rng.normal(0, 1.3, n)
+        d[rng.integers(0, n, n // 10)] = 0.0
+        se_a, p_a = oracle.empirical_null_p(d)
+        se_b, p_b = coracle.empirical_null(d)
+        assert se_a == se_b and np.array_equal(p_a, p_b)
+        lo, hi = oracle.trim_bounds(n)
+        assert abs(se_a - np.std(np.sort(d)[lo - 1:hi], ddof=1)) < 1e-12
+    assert oracle.trim_bounds(30) == (2, 28) and oracle.trim_bounds(19999) == (1000, 18999)
+    with pytest.raises(IndexError):
+        oracle.empirical_null_p(np.zeros(10))  # src:411 BoundsError for r <= 10
+
+
+def test_coin_rule(oracle, coracle):
+    u = oracle.coin_bits(7, 50, 40)
+    for i in (0, 3, 49):
+        for s in (0, 17, 39):
+            assert int(u[i, s]) == coracle.lib().reo_oracle_u(7, i, s)
+    assert 0.4 < u.mean() < 0.6
+    big = oracle.coin_bits(123456789012345, 2000, 64)
+    assert abs(big.mean() - 0.5) < 0.01 and abs(np.corrcoef(big[:-1].ravel(), big[1:].ravel())[0, 1]) < 0.01
+
+
+def test_hand_case_classes(oracle):
+    """n1 = n2 = 8, thr = 8, gene i always greater in group 1 and never in group 2 ->
+    ic = 3, it = 1 -> q = 7 (n31) for gene i and 3 (n13) for gene j."""
+    data = np.array([[9] * 8 + [1] * 8, [5] * 16])
+    gid = np.array([0] * 8 + [1] * 8)
+    thr = np.array([[8, 8], [8, 8]])
+    cat = oracle.pair_categories(data, gid, 2, thr)[0]
+    assert cat[0, 1] == 7 and cat[1, 0] == 3 and cat[0, 0] == 0
+
+
+@pytest.mark.parametrize("seed,r,n1,n2,n3", [(1, 150, 7, 9, 0), (2, 97, 33, 40, 0), (3, 80, 6, 5, 7)])
+def test_numpy_vs_c_identify_degs(oracle, coracle, seed, r, n1, n2, n3):
+    data, group = small_case(seed, r, n1, n2, n3=n3)
+    levels, gid = oracle.group_levels(group)
+    gnum = len(levels)
+    rng = np.random.default_rng(seed)
+    ref = np.zeros(r, bool)
+    ref[rng.choice(r, r // 4, replace=False)] = True
+    a = oracle.identify_degs(data, group, 0.01, 1.0, 0.05, ref, 16, 3, seed=7)
+    thr = coracle.thresholds_for(gid, gnum, 0.01)
+    assert np.array_equal(thr, a["thresholds"])
+    b = coracle.identify_degs(data, gid, gnum, thr, 1.0, 0.05, ref, 16, 3, seed=7)
+    assert a["iters"] == b["iters"]
+    assert np.array_equal(a["result"], b["result"])  # same libm underneath: bit-exact
+    assert np.array_equal(a["updown"], b["updown"]) and np.array_equal(a["final_ref"], b["final_ref"])
+    # invariants (SURVEY 8c iv)
+    cat = oracle.pair_categories(data, gid, gnum, thr, seed=7)
+    for k in range(cat.shape[0]):
+        off = ~np.eye(r, dtype=bool)
+        assert np.all((cat[k] + cat[k].T)[off] == 10)
+    tab = a["result"][0][:, 2:11]
+    fr = a["final_ref"][0].astype(bool)
+    assert np.array_equal(tab.sum(axis=1), fr.sum() - fr.astype(int))
+
+
+def test_golden_small_case(oracle, coracle):
+    g = np.load(os.path.join(GOLDEN, "small_case.npz"))
+    out = coracle.identify_degs(g["data"], g["gid"], 2, g["thr"], 1.0, 0.05, g["ref"], 128, 5, seed=int(g["seed"]))
+    assert out["iters"] == g["iters"].tolist()
+    assert np.array_equal(out["result"], g["result"]) and np.array_equal(out["updown"], g["updown"])
+    grp = ["a" if v == 0 else "b" for v in g["gid"]]
+    a = oracle.identify_degs(g["data"], grp, 0.01, 1.0, 0.05, g["ref"], 128, 5, seed=int(g["seed"]))
+    assert np.array_equal(a["result"], g["result"]) and np.array_equal(a["updown"], g["updown"])
+
+
+def test_golden_bundled_block(coracle):
+    """A 64-row block of the bundled-data fixture, recomputed through the block entry point."""
+    g = np.load(os.path.join(GOLDEN, "bundled_c1.npz"))
+    cols = np.nonzero(g["ref"])[0]
+    # iteration-0 table of rows 1000..1063 against the initial reference set
+    tab, n = coracle.block_tables(g["data"], g["gid"], 2, g["thr"], cols, seed=int(g["seed"]), i0=1000, i1=1064)
+    assert n == 64 * len(cols) * 10
+    refsum = g["ref"].sum() - g["ref"][1000:1064].astype(int)
+    assert np.array_equal(tab.sum(axis=1), refsum)
+    # the final table uses final_ref
+    cols2 = np.nonzero(g["final_ref"])[0]
+    tab2, _ = coracle.block_tables(g["data"], g["gid"], 2, g["thr"], cols2, seed=int(g["seed"]), i0=1000, i1=1064)
+    assert np.array_equal(tab2, g["tables"][1000:1064])
