@@ -3,6 +3,7 @@
 // reads back three counters per evaluation; every number in the result is computed on the device.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -89,6 +90,19 @@ int fail_cuda(reo_handle_t h, cudaError_t e, const char* what) {
     do {                                                             \
         cudaError_t _e = (call);                                     \
         if (_e != cudaSuccess) return fail_cuda(h, _e, #call);       \
+    } while (0)
+
+// REO_DEBUG=1: synchronise after every kernel launch and name the kernel that faulted
+bool debug_sync() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("REO_DEBUG"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }
+    return v == 1;
+}
+#define CKL(call)                                                                  \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e == cudaSuccess && debug_sync()) _e = cudaDeviceSynchronize();       \
+        if (_e != cudaSuccess) return fail_cuda(h, _e, #call);                     \
     } while (0)
 
 size_t dtype_size(int dtype) {
@@ -210,7 +224,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
             CK(cudaMemcpy2DAsync(D.raw.p + (size_t)c0 * r * es, (size_t)r * es, (const uint8_t*)data + (size_t)c0 * ld * es,
                                  (size_t)ld * es, (size_t)r * es, (size_t)nc, cudaMemcpyHostToDevice, D.st));
         }
-        CK(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, c0, (int)nc, D.slot_of_sample.p, D.ranks.p, rpad,
+        CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, c0, (int)nc, D.slot_of_sample.p, D.ranks.p, rpad,
                                    D.flags.p + 2, D.flags.p, D.fblist.p, D.st));
         h->kernel_launches++;
     }
@@ -229,7 +243,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         CK(D.fb_rank.ensure((size_t)batch * rp2));
         for (int b0 = 0; b0 < nfb; b0 += batch) {
             const int nb = std::min(batch, nfb - b0);
-            CK(reo_launch_rank_fallback(dev_data, dtype, r, dev_ld, D.fblist.p + b0, nb, D.slot_of_sample.p, D.ranks.p,
+            CKL(reo_launch_rank_fallback(dev_data, dtype, r, dev_ld, D.fblist.p + b0, nb, D.slot_of_sample.p, D.ranks.p,
                                         rpad, D.flags.p + 2, D.fb_keys.p, D.fb_rank.p, rp2, D.st));
             h->kernel_launches++;
         }
@@ -243,7 +257,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     S.B = B; S.NP = B + 1;
     CK(D.planes.ensure((size_t)S.NT * S.tile_stride()));
     S.planes = D.planes.p;
-    CK(reo_launch_bitplanes(D.ranks.p, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
+    CKL(reo_launch_bitplanes(D.ranks.p, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
                             (uint32_t)(h->seed >> 32), S.planes, D.st));
     h->kernel_launches++;
     // identity column list for "all genes are references"
@@ -280,7 +294,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     const uint32_t* colp = S.planes;
     if (!all_genes) {
         CK(D.panel.ensure((size_t)ntc * S.tile_stride()));
-        CK(reo_launch_gather_panel(S.planes, S.W, S.NP, col_gene_dev, ntc, D.panel.p, D.st));
+        CKL(reo_launch_gather_panel(S.planes, S.W, S.NP, col_gene_dev, ntc, D.panel.p, D.st));
         h->kernel_launches++;
         colp = D.panel.p;
     }
@@ -306,7 +320,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
         D.pev.push_back(a); D.pev.push_back(b);
     }
     CK(cudaEventRecord(D.pev[2 * D.n_pev], D.st));
-    CK(reo_launch_pairs(p, D.num_sms, D.st));
+    CKL(reo_launch_pairs(p, D.num_sms, D.st));
     CK(cudaEventRecord(D.pev[2 * D.n_pev + 1], D.st));
     D.n_pev++;
     h->pair_launches++; h->kernel_launches++;
@@ -318,7 +332,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
 // full build for the mask in mask_dev
 int build_tables_full(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* mask_dev) {
     const ReoStaged& S = D.S;
-    CK(reo_launch_mask_to_list(mask_dev, S.r, D.col_gene.p, D.counts.p + 4, D.st));
+    CKL(reo_launch_mask_to_list(mask_dev, S.r, D.col_gene.p, D.counts.p + 4, D.st));
     h->kernel_launches++;
     CK(cudaMemcpyAsync(D.h_counts + 4, D.counts.p + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
     CK(cudaMemsetAsync(D.table.p, 0, (size_t)D.table_rows * 9 * sizeof(int32_t), D.st));
@@ -468,7 +482,7 @@ int reo_pair_counts(reo_handle_t h, int32_t k, const int32_t* rows, int32_t nrow
     int32_t* d_rows = D.small_i.p; int32_t* d_cols = d_rows + nrows; int32_t* d_nre = d_cols + ncols; int32_t* d_rest = d_nre + n;
     CK(cudaMemcpyAsync(d_rows, rows, nrows * 4, cudaMemcpyHostToDevice, D.st));
     CK(cudaMemcpyAsync(d_cols, cols, ncols * 4, cudaMemcpyHostToDevice, D.st));
-    CK(reo_launch_pair_counts_small(S, D.word_order.p, P.WA, d_rows, nrows, d_cols, ncols, d_nre, d_rest, P.padA, P.padB, D.st));
+    CKL(reo_launch_pair_counts_small(S, D.word_order.p, P.WA, d_rows, nrows, d_cols, ncols, d_nre, d_rest, P.padA, P.padB, D.st));
     CK(cudaMemcpyAsync(nre, d_nre, n * 4, cudaMemcpyDeviceToHost, D.st));
     CK(cudaMemcpyAsync(rest, d_rest, n * 4, cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
@@ -490,7 +504,7 @@ int reo_tables_delta(reo_handle_t h, int32_t k, const int32_t* thresholds, doubl
     if ((rc = build_tables_full(h, D, P, D.mask_a.p))) return rc;
     if (mask_to) {
         CK(cudaMemcpyAsync(D.mask_b.p, mask_to, S.r, cudaMemcpyHostToDevice, D.st));
-        CK(reo_launch_mask_diff(S.r, D.mask_a.p, D.mask_b.p, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
+        CKL(reo_launch_mask_diff(S.r, D.mask_a.p, D.mask_b.p, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
         CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
         if ((rc = launch_tables(h, D, P, D.changed_gene.p, D.changed_sign.p, D.h_counts[2], false))) return rc;
@@ -514,7 +528,7 @@ int reo_mccullagh(reo_handle_t h, const int64_t* tables, int64_t n, int32_t k, d
     CK(D.small_ll.ensure((size_t)n * k * k));
     CK(D.small_d.ensure((size_t)n * 5));
     CK(cudaMemcpyAsync(D.small_ll.p, tables, (size_t)n * k * k * 8, cudaMemcpyHostToDevice, D.st));
-    CK(reo_launch_mccullagh_kxk((const int64_t*)D.small_ll.p, n, k, D.small_d.p, D.st));
+    CKL(reo_launch_mccullagh_kxk((const int64_t*)D.small_ll.p, n, k, D.small_d.p, D.st));
     CK(cudaMemcpyAsync(out, D.small_d.p, (size_t)n * 5 * 8, cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
     return REO_OK;
@@ -528,7 +542,7 @@ int reo_sort_f64(reo_handle_t h, const double* x, int64_t n, double* sorted, int
     CK(D.small_d.ensure((size_t)2 * n));
     CK(D.perm.ensure(n));
     CK(cudaMemcpyAsync(D.small_d.p, x, n * 8, cudaMemcpyHostToDevice, D.st));
-    CK(reo_launch_sort_f64(D.small_d.p, n, D.small_d.p + n, D.perm.p, D.sortws, D.st));
+    CKL(reo_launch_sort_f64(D.small_d.p, n, D.small_d.p + n, D.perm.p, D.sortws, D.st));
     CK(cudaMemcpyAsync(sorted, D.small_d.p + n, n * 8, cudaMemcpyDeviceToHost, D.st));
     if (perm) CK(cudaMemcpyAsync(perm, D.perm.p, n * 4, cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
@@ -544,9 +558,9 @@ int reo_empirical_null(reo_handle_t h, const double* delta1, int64_t n, double* 
     CK(D.small_d.ensure((size_t)3 * n + 1));
     double* d_x = D.small_d.p; double* d_s = d_x + n; double* d_p = d_s + n; double* d_se = d_p + n;
     CK(cudaMemcpyAsync(d_x, delta1, n * 8, cudaMemcpyHostToDevice, D.st));
-    CK(reo_launch_sort_f64(d_x, n, d_s, nullptr, D.sortws, D.st));
-    CK(reo_launch_trimmed_std(d_s, n, d_se, nullptr, D.st));
-    CK(reo_launch_null_pvals(d_x, n, d_se, d_p, D.st));
+    CKL(reo_launch_sort_f64(d_x, n, d_s, nullptr, D.sortws, D.st));
+    CKL(reo_launch_trimmed_std(d_s, n, d_se, nullptr, D.st));
+    CKL(reo_launch_null_pvals(d_x, n, d_se, d_p, D.st));
     CK(cudaMemcpyAsync(pval, d_p, n * 8, cudaMemcpyDeviceToHost, D.st));
     if (se) CK(cudaMemcpyAsync(se, d_se, 8, cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
@@ -563,8 +577,8 @@ int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj) {
     double* d_x = D.small_d.p; double* d_s = d_x + n; double* d_q = d_s + n;
     CK(cudaMemcpyAsync(d_x, p, n * 8, cudaMemcpyHostToDevice, D.st));
     if (n > 1) {
-        CK(reo_launch_sort_f64(d_x, n, d_s, D.perm.p, D.sortws, D.st));
-        CK(reo_launch_bh(d_s, D.perm.p, n, d_q, nullptr, D.st));
+        CKL(reo_launch_sort_f64(d_x, n, d_s, D.perm.p, D.sortws, D.st));
+        CKL(reo_launch_bh(d_s, D.perm.p, n, d_q, nullptr, D.st));
     } else {
         d_q = d_x;
     }
@@ -620,17 +634,17 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             }
             if ((rc = allgather_tables(h, D))) return rc;
             // src:402-406
-            CK(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
+            CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
             // src:409-412
-            CK(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, nullptr, D.sortws, D.st));
-            CK(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, nullptr, D.st));
-            CK(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));
+            CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, nullptr, D.sortws, D.st));
+            CKL(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, nullptr, D.st));
+            CKL(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));
             // src:413
-            CK(reo_launch_sort_f64(D.result.p, r, D.sorted_p.p, D.perm.p, D.sortws, D.st));
-            CK(reo_launch_bh(D.sorted_p.p, D.perm.p, r, D.result.p + r, nullptr, D.st));
+            CKL(reo_launch_sort_f64(D.result.p, r, D.sorted_p.p, D.perm.p, D.sortws, D.st));
+            CKL(reo_launch_bh(D.sorted_p.p, D.perm.p, r, D.result.p + r, nullptr, D.st));
             // src:417
-            CK(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));
-            CK(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
+            CKL(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));
+            CKL(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
             h->kernel_launches += 10;
             CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
             CK(cudaStreamSynchronize(D.st));
@@ -655,7 +669,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             }
         }
         if (n_eval == 0) CK(cudaMemsetAsync(D.result.p, 0, (size_t)r * 15 * sizeof(double), D.st));
-        CK(reo_launch_updown(D.result.p, r, pval_deg, padj_deg, D.updown.p, D.st));
+        CKL(reo_launch_updown(D.result.p, r, pval_deg, padj_deg, D.updown.p, D.st));
         h->kernel_launches++;
         CK(cudaMemcpyAsync(res_host.data() + (size_t)k * r * 15, D.result.p, (size_t)r * 15 * 8, cudaMemcpyDeviceToHost, D.st));
         CK(cudaMemcpyAsync(ud_host.data() + (size_t)k * r, D.updown.p, r, cudaMemcpyDeviceToHost, D.st));

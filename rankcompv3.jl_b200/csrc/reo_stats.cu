@@ -230,32 +230,49 @@ cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int3
 #define STD_MAX_LEAVES 256
 #define STD_THREADS 256
 
-__device__ double std_combine(int64_t lo, int64_t hi, const double* leaf, int* next) {
-    if (lo == hi || hi - lo < 1024) return leaf[(*next)++];
-    const int64_t mid = lo + ((hi - lo) >> 1);
-    const double v1 = std_combine(lo, mid, leaf, next);
-    const double v2 = std_combine(mid + 1, hi, leaf, next);
-    return v1 + v2;
+struct StdFrame { int64_t lo, hi; int state; double v1; };
+
+// Post-order evaluation of Julia's pairwise tree without device recursion (explicit frame stack):
+// value(lo,hi) = leaf | value(lo,mid) + value(mid+1,hi).  Leaves are consumed left to right.
+__device__ double std_combine(int64_t lo0, int64_t hi0, const double* leaf, StdFrame* fr) {
+    int sp = 0, next = 0;
+    double ret = 0.0;
+    fr[sp].lo = lo0; fr[sp].hi = hi0; fr[sp].state = 0; fr[sp].v1 = 0.0; ++sp;
+    while (sp > 0) {
+        StdFrame& f = fr[sp - 1];
+        const int64_t mid = f.lo + ((f.hi - f.lo) >> 1);
+        if (f.state == 0) {
+            if (f.lo == f.hi || f.hi - f.lo < 1024) { ret = leaf[next++]; --sp; }
+            else { f.state = 1; fr[sp].lo = f.lo; fr[sp].hi = mid; fr[sp].state = 0; fr[sp].v1 = 0.0; ++sp; }
+        } else if (f.state == 1) {
+            f.v1 = ret; f.state = 2;
+            fr[sp].lo = mid + 1; fr[sp].hi = f.hi; fr[sp].state = 0; fr[sp].v1 = 0.0; ++sp;
+        } else {
+            ret = f.v1 + ret; --sp;
+        }
+    }
+    return ret;
 }
 
 __global__ void __launch_bounds__(STD_THREADS)
 trimmed_std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ se_out) {
     __shared__ int64_t llo[STD_MAX_LEAVES], lhi[STD_MAX_LEAVES];
     __shared__ double lsum[STD_MAX_LEAVES];
+    __shared__ StdFrame frames[64];
     __shared__ int nleaf;
     __shared__ double mean_s;
     if (threadIdx.x == 0) {
-        int64_t slo[64], shi[64];
+        // enumerate the leaves of the reduction tree left to right (explicit DFS stack in `frames`)
         int sp = 0, nl = 0;
-        slo[0] = lo0; shi[0] = hi0; sp = 1;
+        frames[0].lo = lo0; frames[0].hi = hi0; sp = 1;
         while (sp > 0) {
             --sp;
-            const int64_t lo = slo[sp], hi = shi[sp];
+            const int64_t lo = frames[sp].lo, hi = frames[sp].hi;
             if (lo == hi || hi - lo < 1024) { llo[nl] = lo; lhi[nl] = hi; ++nl; }
             else {
                 const int64_t mid = lo + ((hi - lo) >> 1);
-                slo[sp] = mid + 1; shi[sp] = hi; ++sp;   // right is popped after left
-                slo[sp] = lo; shi[sp] = mid; ++sp;
+                frames[sp].lo = mid + 1; frames[sp].hi = hi; ++sp;   // right is popped after left
+                frames[sp].lo = lo; frames[sp].hi = mid; ++sp;
             }
         }
         nleaf = nl;
@@ -281,8 +298,7 @@ trimmed_std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, 
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            int next = 0;
-            const double tot = std_combine(lo0, hi0, lsum, &next);
+            const double tot = std_combine(lo0, hi0, lsum, frames);
             if (pass == 0) mean_s = tot / (double)m;
             else *se_out = sqrt(tot / (double)(m - 1));
         }
