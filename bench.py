@@ -288,7 +288,8 @@ def main():
                     "d2h_bytes_per_step": int(r * 15 * 8 + 2 * r)},
             "gpu_launches": int(sum(s["kernel_launches"] for s in st_dev)),
             "stage_ms": {"staging": st_dev[-1]["ms_stage"], "pairs": st_dev[-1]["ms_pairs"],
-                         "stats": st_dev[-1]["ms_stats"], "total_device": st_dev[-1]["ms_total"]},
+                         "stats": st_dev[-1]["ms_stats"], "total_device": st_dev[-1]["ms_total"],
+                         "call_wall": st_dev[-1]["ms_wall"]},
             "clocks": clocks, "roofline": roof,
         }
         if not args.no_cpu_baseline:

@@ -68,6 +68,7 @@ typedef struct {
     double ms_pairs;                    /* pair-count/class/table kernels (all iterations)          */
     double ms_stats;                    /* McCullagh + empirical null + BH + mask kernels           */
     double ms_total;                    /* whole call, device timeline                              */
+    double ms_wall;                     /* whole call, host wall clock                              */
     int32_t pair_launches;              /* pair-kernel launches                                     */
     int32_t kernel_launches;            /* all kernel launches of this call                         */
 } reo_stats;

@@ -43,6 +43,7 @@ class ReoStats(C.Structure):
         ("ms_pairs", C.c_double),
         ("ms_stats", C.c_double),
         ("ms_total", C.c_double),
+        ("ms_wall", C.c_double),
         ("pair_launches", C.c_int32),
         ("kernel_launches", C.c_int32),
     ]

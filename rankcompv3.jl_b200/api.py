@@ -165,9 +165,9 @@ class Reo:
             raise ValueError("DimensionMismatch: 'ref_gene' and 'data' do not have compatiable sizes")
         K = 1 if gnum == 2 else max(int(gnum), 1)
         thr = None if thresholds is None else np.asfortranarray(np.asarray(thresholds, dtype=np.int32))
-        result = np.zeros((K, 15, r), dtype=np.float64)  # column-major r x 15 per k
-        updown = np.zeros((K, r), dtype=np.int8)
-        final_ref = np.zeros((K, r), dtype=np.uint8)
+        result = np.empty((K, 15, r), dtype=np.float64)  # column-major r x 15 per k, filled by the library
+        updown = np.empty((K, r), dtype=np.int8)
+        final_ref = np.empty((K, r), dtype=np.uint8)
         iters = np.zeros(K, dtype=np.int32)
         st = L.ReoStats()
         rc = self._lib.reo_identify_degs(self._h, p, dt, r, c, ld, _ptr(gid), int(gnum), _ptr(thr), float(pval_reo),
@@ -179,10 +179,10 @@ class Reo:
         stats = dict(iters_done=int(st.iters_done), converged=int(st.converged), n_deg=list(st.n_deg[:ne]),
                      n_ref=list(st.n_ref[:ne]), rank_bits=int(st.rank_bits), sample_words=int(st.sample_words),
                      compares=int(st.compares), ms_stage=st.ms_stage, ms_pairs=st.ms_pairs, ms_stats=st.ms_stats,
-                     ms_total=st.ms_total, pair_launches=int(st.pair_launches),
+                     ms_total=st.ms_total, ms_wall=st.ms_wall, pair_launches=int(st.pair_launches),
                      kernel_launches=int(st.kernel_launches))
-        return DegResult(np.ascontiguousarray(result.transpose(0, 2, 1)), updown, final_ref,
-                         [int(v) for v in iters], stats)
+        # [K, r, 15] view of the library's column-major output (no copy)
+        return DegResult(result.transpose(0, 2, 1), updown, final_ref, [int(v) for v in iters], stats)
 
     # -- stage-level entry points -----------------------------------------------------------------
     def stage(self, data, group_id, gnum):

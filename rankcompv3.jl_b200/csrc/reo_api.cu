@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <string>
@@ -49,7 +50,7 @@ struct ReoDev {
         fblist, small_i;
     DBuf<int8_t> changed_sign, updown;
     DBuf<uint8_t> mask_a, mask_b;
-    DBuf<double> result, sorted, sorted_p, se, small_d;
+    DBuf<double> result, sorted, sorted_p, se, small_d, std_ws;
     DBuf<unsigned int> counter;
     DBuf<int> flags;
     DBuf<unsigned long long> fb_keys;
@@ -57,9 +58,12 @@ struct ReoDev {
     DBuf<long long> small_ll;
     ReoSortWs sortws;
     int32_t* h_counts = nullptr;  // pinned
+    uint8_t* h_out = nullptr;     // pinned staging for results (grow-only)
+    size_t h_out_cap = 0;
     int table_rows = 0;           // rows allocated in `table`
     std::vector<cudaEvent_t> pev; // event pairs bracketing every pair-kernel launch of the current call
     int n_pev = 0;
+    int64_t iota_r = -1;
 };
 
 struct reo_handle_s {
@@ -136,24 +140,64 @@ long double two_sided_binom_p(int n, int x) {  // HypothesisTests.pvalue(Binomia
 
 struct LevelPlan {  // the two-group view of level k
     int WA = 0, nA = 0, nB = 0, padA = 0, padB = 0, thrA = 0, thrB = 0;
+    int mixed = 0;
+    uint32_t maskA = 0, maskB = 0;
+    int segA0 = 0, mixedW = 0, segB0 = 0, segB0len = 0, segB1 = 0;
     std::vector<int32_t> word_order;
 };
 
 LevelPlan make_plan(const ReoStaged& S, int k, const int32_t* thresholds, double pval_reo) {
     LevelPlan P;
+    P.nA = S.lev_n[k];
+    P.nB = (int)S.c - P.nA;
     for (int w = 0; w < S.lev_words[k]; ++w) P.word_order.push_back(S.lev_word0[k] + w);
     P.WA = S.lev_words[k];
+    if (S.mixed_word >= 0) {
+        // two levels whose tails share one word: [full words of A][mixed][full words of B], no pad slots counted
+        P.word_order.push_back(S.mixed_word);
+        P.mixed = 1;
+        const uint32_t m0 = (S.mixed_rem[0] >= 32) ? 0xffffffffu : ((1u << S.mixed_rem[0]) - 1u);
+        const uint32_t m1 = ((S.mixed_rem[1] >= 32) ? 0xffffffffu : ((1u << S.mixed_rem[1]) - 1u)) << S.mixed_rem[0];
+        P.maskA = (k == 0) ? m0 : m1;
+        P.maskB = (k == 0) ? m1 : m0;
+    }
     for (int g = 0; g < S.gnum; ++g) {
         if (g == k) continue;
         for (int w = 0; w < S.lev_words[g]; ++w) P.word_order.push_back(S.lev_word0[g] + w);
-        P.padB += S.lev_words[g] * 32 - S.lev_n[g];
+        if (S.mixed_word < 0) P.padB += S.lev_words[g] * 32 - S.lev_n[g];
     }
-    P.nA = S.lev_n[k];
-    P.nB = (int)S.c - P.nA;
-    P.padA = S.lev_words[k] * 32 - P.nA;
+    if (S.mixed_word < 0) P.padA = S.lev_words[k] * 32 - P.nA;
+    // the same order as arithmetic segments (levels are staged in order, so "all other levels" is the run
+    // before level k followed by the run after it)
+    P.segA0 = S.lev_word0[k];
+    P.mixedW = S.mixed_word < 0 ? 0 : S.mixed_word;
+    {
+        const int after = S.lev_word0[k] + S.lev_words[k] + (S.mixed_word >= 0 && k == 0 ? 1 : 0);
+        if (S.mixed_word >= 0) {           // two levels: the other level is one run
+            P.segB0 = S.lev_word0[1 - k]; P.segB0len = S.lev_words[1 - k]; P.segB1 = 0;
+        } else {
+            P.segB0 = 0; P.segB0len = S.lev_word0[k]; P.segB1 = after;
+        }
+    }
     if (thresholds) { P.thrA = thresholds[0 + 2 * k]; P.thrB = thresholds[1 + 2 * k]; }
     else { P.thrA = reo_threshold(P.nA, pval_reo); P.thrB = reo_threshold(P.nB, pval_reo); }
     return P;
+}
+
+int ensure_std_ws(reo_handle_t h, ReoDev& D) {
+    if (D.std_ws.p) return REO_OK;
+    CK(D.std_ws.ensure(264));
+    CK(cudaMemsetAsync(D.std_ws.p, 0, 264 * sizeof(double), D.st));
+    return REO_OK;
+}
+
+int ensure_h_out(reo_handle_t h, ReoDev& D, size_t bytes) {
+    if (bytes <= D.h_out_cap) return REO_OK;
+    if (D.h_out) cudaFreeHost(D.h_out);
+    D.h_out = nullptr; D.h_out_cap = 0;
+    CK(cudaMallocHost((void**)&D.h_out, bytes));
+    D.h_out_cap = bytes;
+    return REO_OK;
 }
 
 int upload_plan(reo_handle_t h, ReoDev& D, const LevelPlan& P) {
@@ -186,7 +230,18 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     S.lev_n = lev_n;
     S.lev_words.assign(gnum, 0); S.lev_word0.assign(gnum, 0);
     int W = 0;
-    for (int g = 0; g < gnum; ++g) { S.lev_word0[g] = W; S.lev_words[g] = (lev_n[g] + 31) / 32; W += S.lev_words[g]; }
+    S.mixed_word = -1; S.mixed_rem[0] = S.mixed_rem[1] = 0;
+    const int rem0 = lev_n[0] % 32, rem1 = gnum == 2 ? lev_n[1] % 32 : 0;
+    if (gnum == 2 && rem0 > 0 && rem1 > 0 && rem0 + rem1 <= 32) {
+        // [full words of level 0][one word with both tails][full words of level 1]
+        S.lev_word0[0] = 0; S.lev_words[0] = lev_n[0] / 32;
+        S.mixed_word = S.lev_words[0];
+        S.lev_word0[1] = S.mixed_word + 1; S.lev_words[1] = lev_n[1] / 32;
+        S.mixed_rem[0] = rem0; S.mixed_rem[1] = rem1;
+        W = S.lev_words[0] + 1 + S.lev_words[1];
+    } else {
+        for (int g = 0; g < gnum; ++g) { S.lev_word0[g] = W; S.lev_words[g] = (lev_n[g] + 31) / 32; W += S.lev_words[g]; }
+    }
     S.W = W;
     const int64_t nslots = (int64_t)W * 32;
     const int64_t rpad = (int64_t)S.NT * REO_TILE;
@@ -195,7 +250,10 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         std::vector<int> fill(gnum, 0);
         for (int64_t s = 0; s < c; ++s) {
             const int g = group_id[s];
-            const int32_t slot = S.lev_word0[g] * 32 + fill[g]++;
+            const int f = fill[g]++;
+            int32_t slot = S.lev_word0[g] * 32 + f;
+            if (S.mixed_word >= 0 && f >= S.lev_words[g] * 32)  // tail sample -> the shared word
+                slot = S.mixed_word * 32 + (g == 0 ? 0 : S.mixed_rem[0]) + (f - S.lev_words[g] * 32);
             slot_of_sample[s] = slot; sample_of_slot[slot] = (int32_t)s;
         }
     }
@@ -260,13 +318,14 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     CKL(reo_launch_bitplanes(D.ranks.p, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
                             (uint32_t)(h->seed >> 32), S.planes, D.st));
     h->kernel_launches++;
-    // identity column list for "all genes are references"
-    {
+    // identity column list for "all genes are references" (cached while r is unchanged)
+    if (D.iota_r != r) {
         std::vector<int32_t> iota(rpad, -1);
         for (int64_t i = 0; i < r; ++i) iota[i] = (int32_t)i;
         CK(D.iota.ensure(rpad));
         CK(cudaMemcpyAsync(D.iota.p, iota.data(), rpad * 4, cudaMemcpyHostToDevice, D.st));
         CK(cudaStreamSynchronize(D.st));  // iota is a host temporary
+        D.iota_r = r;
     }
     CK(D.col_gene.ensure(rpad));
     CK(D.changed_gene.ensure(rpad));
@@ -302,7 +361,8 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     ReoPairParams p;
     memset(&p, 0, sizeof(p));
     p.row_planes = S.planes; p.col_planes = colp; p.col_gene = col_gene_dev; p.col_sign = col_sign_dev;
-    p.word_order = D.word_order.p; p.table = D.table.p; p.counter = D.counter.p;
+    p.segA0 = P.segA0; p.mixedW = P.mixedW; p.segB0 = P.segB0; p.segB0len = P.segB0len; p.segB1 = P.segB1;
+    p.table = D.table.p; p.counter = D.counter.p;
     p.W = S.W; p.WA = P.WA; p.NP = S.NP; p.r = (int)S.r;
     p.t0 = std::min(S.NT, h->rank * tpr); p.t1 = std::min(S.NT, (h->rank + 1) * tpr);
     p.ntc = ntc;
@@ -313,6 +373,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     p.jchunk = (ntc + njc - 1) / njc;
     p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;
     p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
+    p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;
     CK(cudaMemsetAsync(D.counter.p, 0, sizeof(unsigned int), D.st));
     if ((size_t)(2 * D.n_pev + 2) > D.pev.size()) {
         cudaEvent_t a, b;
@@ -412,6 +473,8 @@ int reo_destroy(reo_handle_t h) {
         if (D.sortws.keys) cudaFree(D.sortws.keys);
         if (D.sortws.idx) cudaFree(D.sortws.idx);
         if (D.h_counts) cudaFreeHost(D.h_counts);
+        if (D.h_out) cudaFreeHost(D.h_out);
+        D.std_ws.release();
         for (auto& ev : D.ev) if (ev) cudaEventDestroy(ev);
         for (auto& ev : D.pev) cudaEventDestroy(ev);
         if (D.st) cudaStreamDestroy(D.st);
@@ -482,7 +545,8 @@ int reo_pair_counts(reo_handle_t h, int32_t k, const int32_t* rows, int32_t nrow
     int32_t* d_rows = D.small_i.p; int32_t* d_cols = d_rows + nrows; int32_t* d_nre = d_cols + ncols; int32_t* d_rest = d_nre + n;
     CK(cudaMemcpyAsync(d_rows, rows, nrows * 4, cudaMemcpyHostToDevice, D.st));
     CK(cudaMemcpyAsync(d_cols, cols, ncols * 4, cudaMemcpyHostToDevice, D.st));
-    CKL(reo_launch_pair_counts_small(S, D.word_order.p, P.WA, d_rows, nrows, d_cols, ncols, d_nre, d_rest, P.padA, P.padB, D.st));
+    CKL(reo_launch_pair_counts_small(S, D.word_order.p, P.WA, d_rows, nrows, d_cols, ncols, d_nre, d_rest, P.padA, P.padB, P.mixed, P.maskA,
+                                     P.maskB, D.st));
     CK(cudaMemcpyAsync(nre, d_nre, n * 4, cudaMemcpyDeviceToHost, D.st));
     CK(cudaMemcpyAsync(rest, d_rest, n * 4, cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
@@ -559,7 +623,8 @@ int reo_empirical_null(reo_handle_t h, const double* delta1, int64_t n, double* 
     double* d_x = D.small_d.p; double* d_s = d_x + n; double* d_p = d_s + n; double* d_se = d_p + n;
     CK(cudaMemcpyAsync(d_x, delta1, n * 8, cudaMemcpyHostToDevice, D.st));
     CKL(reo_launch_sort_f64(d_x, n, d_s, nullptr, D.sortws, D.st));
-    CKL(reo_launch_trimmed_std(d_s, n, d_se, nullptr, D.st));
+    { int rc2 = ensure_std_ws(h, D); if (rc2) return rc2; }
+    CKL(reo_launch_trimmed_std(d_s, n, d_se, D.std_ws.p, D.st));
     CKL(reo_launch_null_pvals(d_x, n, d_se, d_p, D.st));
     CK(cudaMemcpyAsync(pval, d_p, n * 8, cudaMemcpyDeviceToHost, D.st));
     if (se) CK(cudaMemcpyAsync(se, d_se, 8, cudaMemcpyDeviceToHost, D.st));
@@ -597,6 +662,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     if (gnum < 2) return fail(h, REO_ERR_DIM, "Only 1 level in 'group', at least 2 levels!");
     if (r <= 10) return fail(h, REO_ERR_BOUNDS, "BoundsError: r <= 10 (src:411)");
     ReoDev& D = h->devs[0];
+    const auto wall0 = std::chrono::steady_clock::now();
     CK(cudaSetDevice(D.dev));
     h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0;
     cudaEvent_t e_start = D.ev[0], e_staged = D.ev[1], e_end = D.ev[2];
@@ -609,13 +675,16 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     const int K = gnum == 2 ? 1 : gnum;
     CK(D.result.ensure((size_t)r * 15));
     CK(D.sorted.ensure(r)); CK(D.sorted_p.ensure(r)); CK(D.perm.ensure(r)); CK(D.se.ensure(1)); CK(D.updown.ensure(r));
+    if ((rc = ensure_std_ws(h, D))) return rc;
     reo_stats st_local;
     memset(&st_local, 0, sizeof(st_local));
     double ms_pairs = 0.0;
-    // results are assembled in host temporaries so that caller outputs stay untouched on failure
-    std::vector<double> res_host((size_t)K * r * 15);
-    std::vector<int8_t> ud_host((size_t)K * r);
-    std::vector<uint8_t> fr_host((size_t)K * r);
+    // results are assembled in a pinned staging buffer so that caller outputs stay untouched on failure
+    const size_t res_bytes = (size_t)K * r * 15 * sizeof(double);
+    if ((rc = ensure_h_out(h, D, res_bytes + 2 * (size_t)K * r + 64))) return rc;
+    double* res_host = reinterpret_cast<double*>(D.h_out);
+    int8_t* ud_host = reinterpret_cast<int8_t*>(D.h_out + res_bytes);
+    uint8_t* fr_host = D.h_out + res_bytes + (size_t)K * r;
     std::vector<int32_t> it_host(K, 0);
 
     for (int k = 0; k < K; ++k) {
@@ -637,7 +706,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
             // src:409-412
             CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, nullptr, D.sortws, D.st));
-            CKL(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, nullptr, D.st));
+            CKL(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, D.std_ws.p, D.st));
             CKL(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));
             // src:413
             CKL(reo_launch_sort_f64(D.result.p, r, D.sorted_p.p, D.perm.p, D.sortws, D.st));
@@ -671,9 +740,9 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         if (n_eval == 0) CK(cudaMemsetAsync(D.result.p, 0, (size_t)r * 15 * sizeof(double), D.st));
         CKL(reo_launch_updown(D.result.p, r, pval_deg, padj_deg, D.updown.p, D.st));
         h->kernel_launches++;
-        CK(cudaMemcpyAsync(res_host.data() + (size_t)k * r * 15, D.result.p, (size_t)r * 15 * 8, cudaMemcpyDeviceToHost, D.st));
-        CK(cudaMemcpyAsync(ud_host.data() + (size_t)k * r, D.updown.p, r, cudaMemcpyDeviceToHost, D.st));
-        CK(cudaMemcpyAsync(fr_host.data() + (size_t)k * r, mask_cur, r, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(res_host + (size_t)k * r * 15, D.result.p, (size_t)r * 15 * 8, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(ud_host + (size_t)k * r, D.updown.p, r, cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(fr_host + (size_t)k * r, mask_cur, r, cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
         it_host[k] = n_eval;
         st_local.iters_done = n_eval; st_local.converged = converged;
@@ -688,15 +757,16 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         cudaEventElapsedTime(&ms, D.pev[2 * i], D.pev[2 * i + 1]);
         ms_pairs += ms;
     }
-    memcpy(result, res_host.data(), res_host.size() * 8);
-    memcpy(updown, ud_host.data(), ud_host.size());
-    if (final_ref) memcpy(final_ref, fr_host.data(), fr_host.size());
+    memcpy(result, res_host, res_bytes);
+    memcpy(updown, ud_host, (size_t)K * r);
+    if (final_ref) memcpy(final_ref, fr_host, (size_t)K * r);
     if (iters_done) memcpy(iters_done, it_host.data(), K * sizeof(int32_t));
     if (stats) {
         st_local.rank_bits = S.B; st_local.sample_words = S.W; st_local.compares = h->compares;
         st_local.ms_stage = ms_stage; st_local.ms_pairs = ms_pairs; st_local.ms_total = ms_total;
         st_local.ms_stats = ms_total - ms_stage - ms_pairs;
         st_local.pair_launches = h->pair_launches; st_local.kernel_launches = h->kernel_launches;
+        st_local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
         *stats = st_local;
     }
     return REO_OK;

@@ -41,6 +41,9 @@ struct ReoStaged {
     std::vector<int> lev_word0;      // first word of each level
     std::vector<int> lev_words;      // words of each level
     std::vector<int> lev_n;          // real samples of each level
+    // two-level inputs only: the tails (n % 32) of both levels share one word when they fit
+    int mixed_word = -1;             // index of that word, -1 if none
+    int mixed_rem[2] = {0, 0};       // level 0 occupies bits [0, rem0), level 1 bits [rem0, rem0 + rem1)
     bool valid = false;
     size_t word_stride() const { return (size_t)NP * REO_TILE; }
     size_t tile_stride() const { return (size_t)W * NP * REO_TILE; }
@@ -52,7 +55,9 @@ struct ReoPairParams {
     const uint32_t* col_planes;  // [NTc][W][NP][64] (panel of compacted columns, may alias row_planes)
     const int32_t* col_gene;     // [NTc*64] gene index of each panel column, -1 = pad
     const int8_t* col_sign;      // [NTc*64] +1/-1 (nullptr -> +1)
-    const int32_t* word_order;   // [W]: the first WA entries are the words of group A (level k)
+    // two-group word order without a table: k < WA -> segA0 + k; then the mixed word (if any); then the
+    // other levels' words: segB0 .. segB0 + segB0len - 1, then segB1 ...
+    int segA0, mixedW, segB0, segB0len, segB1;
     int32_t* table;              // [.. ][9] Int32, += sign per (row gene, category)
     unsigned int* counter;       // dynamic work counter (zeroed before launch)
     int W, WA, NP;
@@ -61,7 +66,11 @@ struct ReoPairParams {
     int ntc;                     // column tiles in the panel
     int jchunk, njchunks;        // column tiles per work item, items per row tile
     int nA, nB, padA, padB, thrA, thrB;
-    unsigned long long* compares;  // optional (nullptr): not used by the kernel
+    int mixed;                   // 1: word_order[WA] holds the tails of BOTH groups (maskA / maskB select them)
+    uint32_t maskA, maskB;
+    int KW;                      // sample words per pipeline slot (set by the launcher)
+    int use_lut, lutSZA, lutSZB; // class lookup tables in shared memory (set by the launcher)
+    unsigned int one;            // == 1 (see mad_acc in reo_pairs.cu)
 };
 
 // kernels / launchers implemented in the .cu files
@@ -70,7 +79,8 @@ struct ReoDev;  // per-device state (reo_api.cu)
 cudaError_t reo_launch_pairs(const ReoPairParams& p, int num_sms, cudaStream_t st);
 cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word_order, int WA, const int32_t* rows,
                                          int nrows, const int32_t* cols, int ncols, int32_t* nre, int32_t* rest,
-                                         int padA, int padB, cudaStream_t st);
+                                         int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB,
+                                         cudaStream_t st);
 
 // staging (reo_stage.cu)
 cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,

@@ -13,22 +13,40 @@
 //     borrow' = (x & ~y) | (~(x ^ y) & borrow)        -- ONE LOP3 (LUT 0xB2) per plane
 // seeded with borrow0 = u_i ^ u_j ^ [i<j], the tie coin, so that equal ranks resolve to the coin
 // and the reference's mirror property (src:385-386) holds bit-exactly.  popc() of the final borrow
-// is the per-thread integer accumulator.  Cost: (B+1) LOP3 + 1 POPC + 1 IADD per 32 ordered
-// (i, j, sample) triples; the ALU (LOP3) pipe is the roofline, no tensor cores.
+// feeds the per-thread integer accumulator through an IMAD (FMA pipe), so the ALU pipe carries
+// almost nothing but the LOP3 chains: (B+1) LOP3 + 1 POPC + 1 IMAD per 32 ordered (i, j, sample)
+// triples.  The ALU (LOP3) pipe is the roofline; no tensor cores.
 //
 // Tiling: CTA = 64 row genes x 64 column genes, 256 threads, 4x4 pairs per thread (16 independent
 // borrow chains per thread hide the 4-cycle ALU latency).  Operand tiles ([plane][64 genes] words)
-// are streamed by cp.async.bulk (UBLKCP) into a 3-stage shared-memory ring guarded by mbarriers;
-// each thread reads its 4 row words and 4 column words per plane with two LDS.128 (bank-conflict
-// free: 8 distinct 16 B row chunks + 4 broadcast column chunks per warp).
+// are streamed by cp.async.bulk (UBLKCP) into a 4-slot shared-memory ring guarded by mbarriers
+// with transaction counts; the warp that is LAST to finish a slot refills it, so no warp ever
+// waits on an "empty" barrier and there is no CTA-wide barrier in the loop.  Each thread reads its
+// 4 row words and 4 column words per plane with two LDS.128 (bank-conflict free).
+// Classification: accumulators count in units of 4, i.e. they ARE byte offsets into small
+// shared-memory lookup tables that turn (count of group A) -> class offset and
+// (class of A, count of group B) -> table bin, so the per-pair epilogue costs loads, not ALU ops
+// (compare-based fallback when the tables would not fit, i.e. thousands of samples per group,
+// where the epilogue is negligible anyway).
 // Work items (row tile x chunk of column tiles) are handed out by an atomic counter to a
-// persistent grid of 2 CTAs per SM; each item accumulates a 64 x 9 table in shared memory and
+// persistent grid of 2 CTAs per SM; each item accumulates a 9 x 64 table in shared memory and
 // flushes it with integer atomics (order independent, exact).
 #include "reo_internal.cuh"
 
 #define PK_THREADS 256
-#define PK_KW 4        // sample words per pipeline stage
-#define PK_NS 3        // pipeline stages
+#define PK_WARPS (PK_THREADS / 32)
+#define PK_NS 4              // ring slots
+#define PK_MAX_KW 4          // sample words per slot (upper bound)
+#define PK_SMEM_BUDGET (100 * 1024)
+#define PK_LUT_MAX_WORDS 4096   // lookup-table words (16 KB) above which the compare path is used
+
+#define PKF_FIRST_J 1
+#define PKF_LAST_J 2
+#define PKF_LAST_ITEM 4
+#define PKF_TERM 8
+
+struct PkMeta { int ti, J, w0, nw, flags, pad0, pad1, pad2; };
+struct PkProd { int count, step, nsteps, ti, jbeg, done, pad0, pad1; };   // producer state (shared memory)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -38,6 +56,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -68,20 +89,48 @@ __device__ __forceinline__ uint32_t lop3_xor3(uint32_t x, uint32_t y, uint32_t c
     asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(x), "r"(y), "r"(c));
     return d;
 }
+// acc + pc * k on the FMA pipe (IMAD), keeping the ALU pipe for the LOP3 chains; k derives from a
+// kernel parameter so that ptxas cannot strength-reduce the multiply into ALU shifts/adds
+__device__ __forceinline__ uint32_t mad_acc(uint32_t pc, uint32_t k, uint32_t acc) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(pc), "r"(k), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PK_THREADS) : "memory"); }
+
+// class of one group from a plain count: 0 (i<j stable), 1 (unstable), 2 (i>j stable); src:376-377
+__device__ __forceinline__ uint32_t reo_class(int cnt, int n, int thr) {
+    return (uint32_t)(cnt >= thr) + (uint32_t)(cnt > n - thr);
+}
 
 // NPT > 0: planes known at compile time (fully unrolled chain); NPT == 0: runtime p.NP.
-template <int NPT>
+// LUT: classification through the shared-memory lookup tables (accumulators are shared-memory addresses).
+template <int NPT, bool LUT>
 __global__ void __launch_bounds__(PK_THREADS, 2) reo_pair_kernel(const ReoPairParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int NP = NPT > 0 ? NPT : p.NP;
+    const int KW = p.KW;
     const int op_words = NP * REO_TILE;                 // words of one operand tile for one sample word
     const uint32_t op_bytes = (uint32_t)op_words * 4u;
-    const int stage_words = 2 * PK_KW * op_words;       // rows then columns
+    const int stage_words = 2 * KW * op_words;          // rows then columns
     uint32_t* stages = reinterpret_cast<uint32_t*>(smem_raw);
-    int32_t* tab_s = reinterpret_cast<int32_t*>(stages + (size_t)PK_NS * stage_words);  // [64][9]
-    uint64_t* full = reinterpret_cast<uint64_t*>(tab_s + REO_TILE * 9 + 2);             // 8-byte aligned below
-    full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full) + 7) & ~uintptr_t(7));
-    int* item_s = reinterpret_cast<int*>(full + PK_NS);
+    int32_t* tab_s = reinterpret_cast<int32_t*>(stages + (size_t)PK_NS * stage_words);      // [9][64]
+    PkMeta* metas = reinterpret_cast<PkMeta*>(tab_s + REO_TILE * 9);                         // 32-byte entries
+    uint64_t* full = reinterpret_cast<uint64_t*>(metas + PK_NS);
+    PkProd* pst = reinterpret_cast<PkProd*>(full + PK_NS);
+    int* slot_cnt = reinterpret_cast<int*>(pst + 1);   // warps done with each ring slot
+    uint32_t* lut = reinterpret_cast<uint32_t*>(slot_cnt + PK_NS);
+    // lut layout (words), o = tie-coin orientation of the pair (0: i>j, 1: i<j), SZA/SZB = slots + 1:
+    //   lutA[o][v]         at o*SZA + v              -> shared-memory ADDRESS of lutB[o][ic*SZB + 0]
+    //   lutB[o][ic*SZB+v]  at 2*SZA + o*3*SZB + ...  -> (3*ic + it) * 256 (byte offset of the bin row)
+    // An accumulator starts as the address of lutA[o][0] and grows by 4 per counted sample, so
+    // "classify group A" is one LDS [acc] and "find the bin" is one more.
+    const int SZA = p.lutSZA, SZB = p.lutSZB;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -92,177 +141,316 @@ __global__ void __launch_bounds__(PK_THREADS, 2) reo_pair_kernel(const ReoPairPa
         for (int s = 0; s < PK_NS; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < REO_TILE * 9; i += PK_THREADS) tab_s[i] = 0;
+    if (LUT) {
+        const uint32_t lutB0 = smem_u32(lut) + (uint32_t)(2 * SZA * 4);
+        for (int i = tid; i < 2 * SZA; i += PK_THREADS) {
+            const int o = i / SZA, v = i - o * SZA;
+            lut[i] = lutB0 + (uint32_t)(o * 3 * SZB * 4) + reo_class(v - o * p.padA, p.nA, p.thrA) * (uint32_t)(SZB * 4);
+        }
+        for (int i = tid; i < 6 * SZB; i += PK_THREADS) {
+            const int o = i / (3 * SZB), rem = i - o * 3 * SZB;
+            const int ic = rem / SZB, v = rem - ic * SZB;
+            lut[2 * SZA + i] = (3u * ic + reo_class(v - o * p.padB, p.nB, p.thrB)) * 256u;
+        }
+    }
     __syncthreads();
 
-    const int nchunks = (p.W + PK_KW - 1) / PK_KW;
-    const size_t word_stride = (size_t)p.NP * REO_TILE;          // allocation stride (runtime NP)
+    const int nchunks = (p.W + KW - 1) / KW;
+    const size_t word_stride = (size_t)p.NP * REO_TILE;
     const size_t tile_stride = (size_t)p.W * word_stride;
-    uint32_t phase_bits = 0;   // one parity bit per stage
-    int issued_total = 0;      // only meaningful in tid 0: steps issued so far (for stage rotation)
-    int consumed_total = 0;
+    const int nitems = (p.t1 - p.t0) * p.njchunks;
 
-    for (;;) {
-        if (tid == 0) *item_s = (int)atomicAdd(p.counter, 1u);
-        for (int i = tid; i < REO_TILE * 9; i += PK_THREADS) tab_s[i] = 0;
-        __syncthreads();
-        const int item = *item_s;
-        const int nitems = (p.t1 - p.t0) * p.njchunks;
-        if (item >= nitems) break;
-        const int ti = p.t0 + item / p.njchunks;
-        const int jbeg = (item % p.njchunks) * p.jchunk;
-        const int jend = min(jbeg + p.jchunk, p.ntc);
-        const int nsteps = (jend - jbeg) * nchunks;
-
-        // producer: issue step `st` of this item into the next ring slot
-        auto issue = [&](int st) {
-            const int J = jbeg + st / nchunks;
-            const int ch = st % nchunks;
-            const int w0 = ch * PK_KW;
-            const int nw = min(PK_KW, p.W - w0);
-            const int slot = issued_total % PK_NS;
-            uint32_t* dst = stages + (size_t)slot * stage_words;
-            mbar_expect_tx(&full[slot], (uint32_t)nw * 2u * op_bytes);
-            for (int kk = 0; kk < nw; ++kk) {
-                const int w = p.word_order[w0 + kk];
-                bulk_g2s(dst + kk * op_words, p.row_planes + (size_t)ti * tile_stride + (size_t)w * word_stride,
-                         op_bytes, &full[slot]);
-                bulk_g2s(dst + (PK_KW + kk) * op_words,
-                         p.col_planes + (size_t)J * tile_stride + (size_t)w * word_stride, op_bytes, &full[slot]);
+    // ---- producer: run by whichever warp is LAST to finish a ring slot (so nobody waits on an "empty"
+    //      barrier); its state lives in shared memory.  k-th word of the two-group order -> staged word:
+    auto word_of = [&](int k) -> int {
+        if (k < p.WA) return p.segA0 + k;
+        k -= p.WA;
+        if (p.mixed) { if (k == 0) return p.mixedW; k -= 1; }
+        return k < p.segB0len ? p.segB0 + k : p.segB1 + (k - p.segB0len);
+    };
+    auto produce_one = [&]() {
+        if (pst->done) return;
+        const int pr_count = pst->count;
+        const int slot = pr_count % PK_NS;
+        PkMeta& m = metas[slot];
+        if (pst->step == pst->nsteps) {
+            const int item = (int)atomicAdd(p.counter, 1u);
+            if (item >= nitems) {
+                m.flags = PKF_TERM;
+                mbar_arrive(&full[slot]);
+                pst->done = 1; pst->count = pr_count + 1;
+                return;
             }
-            issued_total++;
-        };
-        if (tid == 0) {
-            const int pre = min(PK_NS, nsteps);
-            for (int st = 0; st < pre; ++st) issue(st);
+            pst->ti = p.t0 + item / p.njchunks;
+            pst->jbeg = (item % p.njchunks) * p.jchunk;
+            const int jend = min(pst->jbeg + p.jchunk, p.ntc);
+            pst->nsteps = (jend - pst->jbeg) * nchunks;
+            pst->step = 0;
         }
+        const int st = pst->step, ti = pst->ti;
+        const int J = pst->jbeg + st / nchunks;
+        const int ch = st % nchunks;
+        const int w0 = ch * KW;
+        const int nw = min(KW, p.W - w0);
+        m.ti = ti; m.J = J; m.w0 = w0; m.nw = nw;
+        m.flags = (ch == 0 ? PKF_FIRST_J : 0) | (ch == nchunks - 1 ? PKF_LAST_J : 0) |
+                  (st == pst->nsteps - 1 ? PKF_LAST_ITEM : 0);
+        uint32_t* dst = stages + (size_t)slot * stage_words;
+        mbar_expect_tx(&full[slot], (uint32_t)nw * 2u * op_bytes);
+        const uint32_t* rbase = p.row_planes + (size_t)ti * tile_stride;
+        const uint32_t* cbase = p.col_planes + (size_t)J * tile_stride;
+        // one bulk copy per run of consecutive staged words (the whole step when the order is contiguous)
+        int kk = 0;
+        while (kk < nw) {
+            const int w = word_of(w0 + kk);
+            int run = 1;
+            while (kk + run < nw && word_of(w0 + kk + run) == w + run) ++run;
+            bulk_g2s(dst + kk * op_words, rbase + (size_t)w * word_stride, (uint32_t)run * op_bytes, &full[slot]);
+            bulk_g2s(dst + (KW + kk) * op_words, cbase + (size_t)w * word_stride, (uint32_t)run * op_bytes, &full[slot]);
+            kk += run;
+        }
+        pst->step = st + 1; pst->count = pr_count + 1;
+    };
+    if (tid == 0) {
+        pst->count = 0; pst->step = 0; pst->nsteps = 0; pst->ti = 0; pst->jbeg = 0; pst->done = 0;
+        for (int s = 0; s < PK_NS; ++s) { slot_cnt[s] = 0; produce_one(); }
+    }
+    __syncthreads();
 
-        const int gi0 = ti * REO_TILE + ty * 4;
-        int st = 0;
-        for (int J = jbeg; J < jend; ++J) {
-            // per-pair orientation masks: all-ones where row gene index < column gene index
-            uint32_t omask[4][4];
-            int gj[4];
+    // ---- consumers (all 8 warps) ----
+    // Accumulators count in units of 4 (acc = 4 * count [+ carried class offset]).
+    uint32_t acc[4][4];
+    int gj[4];
+    int sgn[4];
+    uint32_t om = 0u;          // tie-coin orientation [i<j] of this thread's pairs (all-ones / zero) ...
+    uint32_t obits = 0u;       // ... and per pair (bit a*4+b), used only when the 4x4 block straddles i == j
+    bool uniform = true, all_valid = false;
+    int gi0 = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) gj[b] = p.col_gene[J * REO_TILE + tx * 4 + b];
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0u;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) omask[a][b] = (gi0 + a < gj[b]) ? 0xffffffffu : 0u;
-            uint32_t acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0u;
-            uint32_t icpack = 0u;
+    for (int b = 0; b < 4; ++b) { gj[b] = -1; sgn[b] = 1; }
+    const uint32_t four = p.one << 2;
+    const uint32_t lut_s = smem_u32(lut);
+    const uint32_t tab_row_s = smem_u32(tab_s) + (uint32_t)(ty * 4) * 4u;   // + bin*256 + a*4
 
-            for (int ch = 0; ch < nchunks; ++ch, ++st) {
-                const int slot = consumed_total % PK_NS;
-                mbar_wait(&full[slot], (phase_bits >> slot) & 1u);
-                phase_bits ^= (1u << slot);
-                const uint32_t* srow = stages + (size_t)slot * stage_words;
-                const uint32_t* scol = srow + PK_KW * op_words;
-                const int w0 = ch * PK_KW;
-                const int nw = min(PK_KW, p.W - w0);
-                for (int kk = 0; kk < nw; ++kk) {
-                    if (w0 + kk == p.WA) {  // group A finished: classify ic, restart the counters
+    // group-A class of a pair -> new accumulator value (count restarts at 0, class carried along)
+    auto flushA = [&](uint32_t acc4, int idx) -> uint32_t {
+        if (LUT) return lds_u32(acc4);
+        const uint32_t o = (obits >> idx) & 1u;
+        return reo_class((int)(acc4 >> 2) - (int)(o * (uint32_t)p.padA), p.nA, p.thrA) << 28;
+    };
+    // (class of A, count of B) -> byte offset of the table bin row
+    auto binB = [&](uint32_t acc4, int idx) -> uint32_t {
+        if (LUT) return lds_u32(acc4);
+        const uint32_t o = (obits >> idx) & 1u;
+        const uint32_t it = reo_class((int)((acc4 & 0x0fffffffu) >> 2) - (int)(o * (uint32_t)p.padB), p.nB, p.thrB);
+        return (3u * (acc4 >> 28) + it) * 256u;
+    };
+
+    for (int cc = 0;; ++cc) {
+        const int slot = cc % PK_NS;
+        mbar_wait(&full[slot], (uint32_t)(cc / PK_NS) & 1u);
+        PkMeta m;   // snapshot now: the slot's metadata is rewritten as soon as the last warp releases it
+        {
+            const volatile PkMeta* vm = &metas[slot];
+            m.ti = vm->ti; m.J = vm->J; m.w0 = vm->w0; m.nw = vm->nw; m.flags = vm->flags;
+        }
+        if (m.flags & PKF_TERM) break;
+        if (m.flags & PKF_FIRST_J) {
+            gi0 = m.ti * REO_TILE + ty * 4;
+            const int4 g4 = *reinterpret_cast<const int4*>(p.col_gene + m.J * REO_TILE + tx * 4);
+            gj[0] = g4.x; gj[1] = g4.y; gj[2] = g4.z; gj[3] = g4.w;
+            if (p.col_sign) {
+                const char4 s4 = *reinterpret_cast<const char4*>(p.col_sign + m.J * REO_TILE + tx * 4);
+                sgn[0] = s4.x; sgn[1] = s4.y; sgn[2] = s4.z; sgn[3] = s4.w;
+            }
+            // columns ascend.  Orientation [i<j] is uniform over the 4x4 block unless it straddles i == j.
+            const bool cols_ok = (gj[0] >= 0) && (gj[3] >= 0);
+            const bool all_lt = cols_ok && (gi0 + 3 < gj[0]);     // every row index below every column index
+            const bool all_ge = cols_ok && (gi0 > gj[3]);         // every row index above every column index
+            uniform = all_lt || all_ge;
+            all_valid = uniform && (gi0 + 3 < p.r);
+            om = all_lt ? 0xffffffffu : 0u;
+            obits = all_lt ? 0xffffu : 0u;
+            if (!uniform) {
 #pragma unroll
-                        for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                const int nre = (int)acc[a][b] - (int)(omask[a][b] & (uint32_t)p.padA);
-                                const uint32_t ic = nre >= p.thrA ? 2u : ((p.nA - nre) >= p.thrA ? 0u : 1u);
-                                icpack |= ic << (2 * (a * 4 + b));
-                                acc[a][b] = 0u;
-                            }
-                    }
-                    const uint32_t* xr = srow + kk * op_words + ty * 4;
-                    const uint32_t* yc = scol + kk * op_words + tx * 4;
-                    uint32_t bor[4][4];
-                    {
-                        const uint4 xv = *reinterpret_cast<const uint4*>(xr);
-                        const uint4 yv = *reinterpret_cast<const uint4*>(yc);
-                        const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                        const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+                    for (int b = 0; b < 4; ++b) obits |= (uint32_t)(gi0 + a < gj[b]) << (a * 4 + b);
+                om = (obits & 1u) ? 0xffffffffu : 0u;
+            }
+            if (LUT) {
+                const uint32_t a0 = lut_s + (om & (uint32_t)(SZA * 4));
 #pragma unroll
-                        for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) bor[a][b] = lop3_xor3(x[a], y[b], omask[a][b]);
-                    }
-                    if (NPT > 0) {
-#pragma unroll
-                        for (int pl = 1; pl < (NPT > 0 ? NPT : 1); ++pl) {
-                            const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
-                            const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
-                            const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                            const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                                for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
-                        }
-                    } else {
-#pragma unroll 2
-                        for (int pl = 1; pl < NP; ++pl) {
-                            const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
-                            const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
-                            const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                            const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                                for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
-                        }
-                    }
+                    for (int b = 0; b < 4; ++b) acc[a][b] = a0;
+                if (!uniform) {
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] += __popc(bor[a][b]);
+                        for (int b = 0; b < 4; ++b) acc[a][b] = lut_s + ((obits >> (a * 4 + b)) & 1u) * (uint32_t)(SZA * 4);
                 }
-                consumed_total++;
-                __syncthreads();  // every thread is done with this ring slot
-                if (tid == 0 && st + PK_NS < nsteps) issue(st + PK_NS);
+            } else {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0u;
             }
-            // group B finished: classify it, add to the shared table
+        }
+        const uint32_t* srow = stages + (size_t)slot * stage_words;
+        const uint32_t* scol = srow + KW * op_words;
+        for (int kk = 0; kk < m.nw; ++kk) {
+            const bool boundary = (m.w0 + kk == p.WA);   // first word that is not a pure group-A word
+            if (boundary && !p.mixed) {
+                // group A finished: classify ic, restart the counters with the class carried along
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = flushA(acc[a][b], a * 4 + b);
+            }
+            const uint32_t* xr = srow + kk * op_words + ty * 4;
+            const uint32_t* yc = scol + kk * op_words + tx * 4;
+            uint32_t bor[4][4];
+            {
+                const uint4 xv = *reinterpret_cast<const uint4*>(xr);
+                const uint4 yv = *reinterpret_cast<const uint4*>(yc);
+                const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
+                const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) bor[a][b] = lop3_xor3(x[a], y[b], om);
+            }
+            if (!uniform) {   // rare: flip the coin seed of the pairs whose orientation differs from pair (0,0)
+                uint32_t ob = obits;
+                asm volatile("" : "+r"(ob));   // keep the mask arithmetic inside this branch
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) bor[a][b] ^= (0u - (((ob >> (a * 4 + b)) ^ ob) & 1u));
+            }
+            if (NPT > 0) {
+#pragma unroll
+                for (int pl = 1; pl < (NPT > 0 ? NPT : 1); ++pl) {
+                    const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
+                    const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
+                    const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                }
+            } else {
+#pragma unroll 2
+                for (int pl = 1; pl < NP; ++pl) {
+                    const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
+                    const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
+                    const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                }
+            }
+            if (boundary && p.mixed) {
+                // the word shared by the tails of both groups: count group A's slots, classify, then
+                // count group B's slots (the masks select real samples only: no pad slots are counted)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t fullA = mad_acc((uint32_t)__popc(bor[a][b] & p.maskA), four, acc[a][b]);
+                        acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b] & p.maskB), four, flushA(fullA, a * 4 + b));
+                    }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b]), four, acc[a][b]);
+            }
+        }
+        if (m.flags & PKF_LAST_J) {
+            // group B finished: look up the bin, add to the shared table
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int gi = gi0 + a;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const int rest = (int)acc[a][b] - (int)(omask[a][b] & (uint32_t)p.padB);
-                    const int it = rest >= p.thrB ? 2 : ((p.nB - rest) >= p.thrB ? 0 : 1);
-                    const int ic = (int)((icpack >> (2 * (a * 4 + b))) & 3u);
-                    if (gj[b] >= 0 && gi != gj[b] && gi < p.r) {
-                        const int sg = p.col_sign ? (int)p.col_sign[J * REO_TILE + tx * 4 + b] : 1;
-                        atomicAdd(&tab_s[(ty * 4 + a) * 9 + ic * 3 + it], sg);
+                    const uint32_t off = binB(acc[a][b], a * 4 + b);
+                    if (all_valid || (gj[b] >= 0 && gi != gj[b] && gi < p.r)) {
+                        const uint32_t addr = tab_row_s + off + (uint32_t)(a * 4);
+                        asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(sgn[b]) : "memory");
                     }
                 }
             }
         }
-        __syncthreads();
-        for (int i = tid; i < REO_TILE * 9; i += PK_THREADS) {
-            const int v = tab_s[i];
-            const int gi = ti * REO_TILE + i / 9;
-            if (v != 0 && gi < p.r) atomicAdd(&p.table[(size_t)gi * 9 + (i % 9)], v);
+        __syncwarp();
+        if (lane == 0) {
+            // the last warp to finish this slot refills it (3 steps ahead of its consumers)
+            if (atomicAdd(&slot_cnt[slot], 1) == PK_WARPS - 1) {
+                slot_cnt[slot] = 0;
+                produce_one();
+            }
         }
-        __syncthreads();
+        if (m.flags & PKF_LAST_ITEM) {
+            consumer_bar();
+            for (int i = tid; i < REO_TILE * 9; i += PK_THREADS) {
+                const int v = tab_s[i];
+                const int gi = m.ti * REO_TILE + (i & 63);
+                if (v != 0 && gi < p.r) atomicAdd(&p.table[(size_t)gi * 9 + (i >> 6)], v);
+                tab_s[i] = 0;
+            }
+            consumer_bar();
+        }
     }
 }
 
-static size_t pair_smem_bytes(int NP) {
-    return (size_t)PK_NS * 2 * PK_KW * NP * REO_TILE * 4 + (REO_TILE * 9 + 2) * 4 + 8 + PK_NS * 8 + 16;
+static void pair_lut_sizes(const ReoPairParams& p, int* sza, int* szb, int* use) {
+    // slots whose borrow bits can be counted for group A / group B (real samples + pad slots) + 1
+    const int a = p.nA + p.padA + 1, b = p.nB + p.padB + 1;
+    *sza = a; *szb = b;
+    *use = (2 * a + 6 * b) <= PK_LUT_MAX_WORDS;
+}
+static int pair_kw(int NP, int W, int lut_words) {
+    int kw = (PK_SMEM_BUDGET - lut_words * 4) / (PK_NS * 2 * NP * REO_TILE * 4);
+    if (kw > PK_MAX_KW) kw = PK_MAX_KW;
+    if (kw > W) kw = W;
+    if (kw < 1) kw = 1;
+    return kw;
+}
+static size_t pair_smem_bytes(int NP, int KW, int lut_words) {
+    return (size_t)PK_NS * 2 * KW * NP * REO_TILE * 4 + REO_TILE * 9 * 4 + PK_NS * sizeof(PkMeta) + PK_NS * 8 +
+           sizeof(PkProd) + PK_NS * 4 + (size_t)lut_words * 4 + 16;
 }
 
-template <int NPT>
-static cudaError_t launch_np(const ReoPairParams& p, int num_sms, cudaStream_t st) {
-    const size_t smem = pair_smem_bytes(p.NP);
-    cudaError_t e = cudaFuncSetAttribute(reo_pair_kernel<NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int NPT, bool LUT>
+static cudaError_t launch_np_lut(const ReoPairParams& p, int lut_words, int num_sms, cudaStream_t st) {
+    const size_t smem = pair_smem_bytes(p.NP, p.KW, lut_words);
+    cudaError_t e = cudaFuncSetAttribute(reo_pair_kernel<NPT, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nitems = (p.t1 - p.t0) * p.njchunks;
     int grid = 2 * num_sms;
     if (grid > nitems) grid = nitems;
     if (grid < 1) return cudaSuccess;
-    reo_pair_kernel<NPT><<<grid, PK_THREADS, smem, st>>>(p);
+    reo_pair_kernel<NPT, LUT><<<grid, PK_THREADS, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int NPT>
+static cudaError_t launch_np(ReoPairParams p, int num_sms, cudaStream_t st) {
+    pair_lut_sizes(p, &p.lutSZA, &p.lutSZB, &p.use_lut);
+    const int lut_words = p.use_lut ? 2 * p.lutSZA + 6 * p.lutSZB : 0;
+    p.KW = pair_kw(p.NP, p.W, lut_words);
+    p.one = 1u;
+    return p.use_lut ? launch_np_lut<NPT, true>(p, lut_words, num_sms, st)
+                     : launch_np_lut<NPT, false>(p, lut_words, num_sms, st);
 }
 
 cudaError_t reo_launch_pairs(const ReoPairParams& p, int num_sms, cudaStream_t st) {
@@ -281,7 +469,7 @@ __global__ void pair_counts_small_kernel(const uint32_t* __restrict__ planes, in
                                          const int32_t* __restrict__ word_order, int WA,
                                          const int32_t* __restrict__ rows, int nrows,
                                          const int32_t* __restrict__ cols, int ncols, int32_t* nre, int32_t* rest,
-                                         int padA, int padB) {
+                                         int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * ncols) return;
     const int gi = rows[idx / ncols], gj = cols[idx % ncols];
@@ -299,7 +487,9 @@ __global__ void pair_counts_small_kernel(const uint32_t* __restrict__ planes, in
             const uint32_t x = xi[(size_t)pl * REO_TILE], y = yj[(size_t)pl * REO_TILE];
             bor = (x & ~y) | (~(x ^ y) & bor);
         }
-        if (k < WA) a += __popc(bor); else b += __popc(bor);
+        if (k == WA && mixed) { a += __popc(bor & maskA); b += __popc(bor & maskB); }
+        else if (k < WA) a += __popc(bor);
+        else b += __popc(bor);
     }
     nre[idx] = a - (int)(om & (uint32_t)padA);
     rest[idx] = b - (int)(om & (uint32_t)padB);
@@ -307,10 +497,10 @@ __global__ void pair_counts_small_kernel(const uint32_t* __restrict__ planes, in
 
 cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word_order, int WA, const int32_t* rows,
                                          int nrows, const int32_t* cols, int ncols, int32_t* nre, int32_t* rest,
-                                         int padA, int padB, cudaStream_t st) {
+                                         int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB, cudaStream_t st) {
     const int n = nrows * ncols;
     if (n <= 0) return cudaSuccess;
     pair_counts_small_kernel<<<(n + 127) / 128, 128, 0, st>>>(S.planes, S.W, S.NP, word_order, WA, rows, nrows, cols,
-                                                              ncols, nre, rest, padA, padB);
+                                                              ncols, nre, rest, padA, padB, mixed, maskA, maskB);
     return cudaGetLastError();
 }

@@ -180,26 +180,45 @@ sort_chunks_kernel(const double* __restrict__ x, int64_t n, unsigned long long* 
     for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) { keys[base + i] = sk[i]; idx[base + i] = si[i]; }
 }
 
-__global__ void sort_rank_kernel(const double* __restrict__ x, int64_t n, int nchunks,
-                                 const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx,
-                                 double* __restrict__ sorted, int32_t* __restrict__ perm) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (int64_t)nchunks * SORT_CHUNK) return;
-    const uint32_t ie = idx[e];
-    if (ie == 0xffffffffu) return;
-    const unsigned long long ke = keys[e];
-    const int mych = (int)(e / SORT_CHUNK);
-    int64_t pos = e - (int64_t)mych * SORT_CHUNK;
+// One CTA per chunk A: every other chunk B is staged in shared memory in turn and each element of A
+// counts the elements of B below it (binary search in shared memory); final position = sum of counts.
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_rank_kernel(const double* __restrict__ x, int64_t n, int nchunks,
+                 const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx,
+                 double* __restrict__ sorted, int32_t* __restrict__ perm) {
+    __shared__ unsigned long long sk[SORT_CHUNK];
+    __shared__ uint32_t si[SORT_CHUNK];
+    const int mych = blockIdx.x;
+    const int64_t base = (int64_t)mych * SORT_CHUNK;
+    constexpr int PER = SORT_CHUNK / SORT_THREADS;
+    unsigned long long ke[PER];
+    uint32_t ie[PER];
+    int pos[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int e = threadIdx.x + q * SORT_THREADS;
+        ke[q] = keys[base + e]; ie[q] = idx[base + e]; pos[q] = e;
+    }
     for (int ch = 0; ch < nchunks; ++ch) {
         if (ch == mych) continue;
-        const unsigned long long* ck = keys + (int64_t)ch * SORT_CHUNK;
-        const uint32_t* ci = idx + (int64_t)ch * SORT_CHUNK;
-        int a = 0, b = SORT_CHUNK;  // number of elements of chunk ch that are < (ke, ie)
-        while (a < b) { const int m = (a + b) >> 1; if (kv_less(ck[m], ci[m], ke, ie)) a = m + 1; else b = m; }
-        pos += a;
+        __syncthreads();
+        for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) {
+            sk[i] = keys[(int64_t)ch * SORT_CHUNK + i]; si[i] = idx[(int64_t)ch * SORT_CHUNK + i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            int a = 0, b = SORT_CHUNK;  // number of elements of chunk ch that are < (ke, ie)
+            while (a < b) { const int m = (a + b) >> 1; if (kv_less(sk[m], si[m], ke[q], ie[q])) a = m + 1; else b = m; }
+            pos[q] += a;
+        }
     }
-    sorted[pos] = x[ie];
-    if (perm) perm[pos] = (int32_t)ie;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        if (ie[q] == 0xffffffffu) continue;
+        sorted[pos[q]] = x[ie[q]];
+        if (perm) perm[pos[q]] = (int32_t)ie[q];
+    }
 }
 
 cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,
@@ -218,7 +237,7 @@ cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int3
         ws.cap = need;
     }
     sort_chunks_kernel<<<nchunks, SORT_THREADS, 0, st>>>(x, n, ws.keys, ws.idx);
-    sort_rank_kernel<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(x, n, nchunks, ws.keys, ws.idx, sorted, perm);
+    sort_rank_kernel<<<nchunks, SORT_THREADS, 0, st>>>(x, n, nchunks, ws.keys, ws.idx, sorted, perm);
     return cudaGetLastError();
 }
 
@@ -228,7 +247,7 @@ cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int3
 // combined in the exact tree order by one thread.
 // ------------------------------------------------------------------------------------------------
 #define STD_MAX_LEAVES 256
-#define STD_THREADS 256
+#define STD_CHUNK 256
 
 struct StdFrame { int64_t lo, hi; int state; double v1; };
 
@@ -254,65 +273,92 @@ __device__ double std_combine(int64_t lo0, int64_t hi0, const double* leaf, StdF
     return ret;
 }
 
-__global__ void __launch_bounds__(STD_THREADS)
-trimmed_std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ se_out) {
-    __shared__ int64_t llo[STD_MAX_LEAVES], lhi[STD_MAX_LEAVES];
-    __shared__ double lsum[STD_MAX_LEAVES];
-    __shared__ StdFrame frames[64];
-    __shared__ int nleaf;
-    __shared__ double mean_s;
-    if (threadIdx.x == 0) {
-        // enumerate the leaves of the reduction tree left to right (explicit DFS stack in `frames`)
-        int sp = 0, nl = 0;
-        frames[0].lo = lo0; frames[0].hi = hi0; sp = 1;
-        while (sp > 0) {
-            --sp;
-            const int64_t lo = frames[sp].lo, hi = frames[sp].hi;
-            if (lo == hi || hi - lo < 1024) { llo[nl] = lo; lhi[nl] = hi; ++nl; }
-            else {
-                const int64_t mid = lo + ((hi - lo) >> 1);
-                frames[sp].lo = mid + 1; frames[sp].hi = hi; ++sp;   // right is popped after left
-                frames[sp].lo = lo; frames[sp].hi = mid; ++sp;
-            }
+// bounds of leaf number `want` (left to right) of the tree over [lo0, hi0]; returns the leaf count
+__device__ int std_leaf_bounds(int64_t lo0, int64_t hi0, int want, int64_t* lo_out, int64_t* hi_out, StdFrame* fr) {
+    int sp = 0, nl = 0;
+    fr[0].lo = lo0; fr[0].hi = hi0; sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int64_t lo = fr[sp].lo, hi = fr[sp].hi;
+        if (lo == hi || hi - lo < 1024) { if (nl == want) { *lo_out = lo; *hi_out = hi; } ++nl; }
+        else {
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            fr[sp].lo = mid + 1; fr[sp].hi = hi; ++sp;   // right is popped after left
+            fr[sp].lo = lo; fr[sp].hi = mid; ++sp;
         }
-        nleaf = nl;
     }
-    __syncthreads();
-    const int64_t m = hi0 - lo0 + 1;
-    for (int pass = 0; pass < 2; ++pass) {
-        const double mean = pass ? mean_s : 0.0;
-        for (int l = threadIdx.x; l < nleaf; l += STD_THREADS) {
-            const int64_t lo = llo[l], hi = lhi[l];
-            double v;
-            if (pass == 0) {
-                if (lo == hi) v = sorted[lo];
-                else { v = sorted[lo] + sorted[lo + 1]; for (int64_t i = lo + 2; i <= hi; ++i) v = v + sorted[i]; }
-            } else {
-                if (lo == hi) v = (sorted[lo] - mean) * (sorted[lo] - mean);
-                else {
-                    v = (sorted[lo] - mean) * (sorted[lo] - mean) + (sorted[lo + 1] - mean) * (sorted[lo + 1] - mean);
-                    for (int64_t i = lo + 2; i <= hi; ++i) v = v + (sorted[i] - mean) * (sorted[i] - mean);
-                }
+    return nl;
+}
+
+// PASS 0: leaf sums of x -> mean.  PASS 1: leaf sums of (x-mean)^2 -> se.  One warp per leaf: lanes
+// stage 256 values at a time in shared memory (coalesced), lane 0 adds them strictly left to right;
+// the last CTA to finish combines the leaves in tree order.  ws: [0..255] leaf sums, [256] mean.
+template <int PASS>
+__global__ void __launch_bounds__(32)
+std_leaf_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ ws,
+                unsigned int* __restrict__ done, double* __restrict__ se_out) {
+    __shared__ double buf[STD_CHUNK];
+    __shared__ StdFrame frames[64];
+    __shared__ int64_t b_lo, b_hi;
+    __shared__ int last;
+    const int lane = threadIdx.x;
+    if (lane == 0) std_leaf_bounds(lo0, hi0, blockIdx.x, &b_lo, &b_hi, frames);
+    __syncwarp();
+    const int64_t lo = b_lo, hi = b_hi;
+    const double mean = PASS ? ws[STD_MAX_LEAVES] : 0.0;
+    double v = 0.0;
+    for (int64_t c0 = lo; c0 <= hi; c0 += STD_CHUNK) {
+        const int cnt = (int)((hi - c0 + 1 < STD_CHUNK) ? hi - c0 + 1 : STD_CHUNK);
+        __syncwarp();
+        for (int i = lane; i < cnt; i += 32) {
+            const double xv = sorted[c0 + i];
+            buf[i] = PASS ? (xv - mean) * (xv - mean) : xv;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int i = 0;
+            if (c0 == lo) {
+                if (cnt == 1) { v = buf[0]; i = 1; }
+                else { v = buf[0] + buf[1]; i = 2; }
             }
-            lsum[l] = v;
+#pragma unroll 8
+            for (; i < cnt; ++i) v = v + buf[i];
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const double tot = std_combine(lo0, hi0, lsum, frames);
-            if (pass == 0) mean_s = tot / (double)m;
-            else *se_out = sqrt(tot / (double)(m - 1));
-        }
-        __syncthreads();
+    }
+    if (lane == 0) {
+        ws[blockIdx.x] = v;
+        __threadfence();
+        last = (atomicAdd(done, 1u) == gridDim.x - 1);
+    }
+    __syncwarp();
+    if (last && lane == 0) {
+        __threadfence();
+        const volatile double* vw = ws;
+        double* leaf = buf;  // reuse shared memory for the leaf sums (<= 256)
+        for (int l = 0; l < (int)gridDim.x; ++l) leaf[l] = vw[l];
+        const double tot = std_combine(lo0, hi0, leaf, frames);
+        const int64_t m = hi0 - lo0 + 1;
+        if (PASS == 0) ws[STD_MAX_LEAVES] = tot / (double)m;
+        else *se_out = sqrt(tot / (double)(m - 1));
+        *done = 0u;
     }
 }
 
-cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* /*leaf_ws*/,
-                                   cudaStream_t st) {
+static int std_count_leaves(int64_t lo, int64_t hi) {
+    if (lo == hi || hi - lo < 1024) return 1;
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    return std_count_leaves(lo, mid) + std_count_leaves(mid + 1, hi);
+}
+
+cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* ws, cudaStream_t st) {
     // round(Int, r*0.05) : round(Int, r*0.95), 1-based inclusive, round-half-even on the FP64 product
     const int64_t lo = (int64_t)nearbyint((double)n * 0.05), hi = (int64_t)nearbyint((double)n * 0.95);
-    if (lo < 1 || hi > n || hi < lo) return cudaErrorInvalidValue;
-    if ((hi - lo + 1) / 512 + 2 > STD_MAX_LEAVES) return cudaErrorInvalidValue;
-    trimmed_std_kernel<<<1, STD_THREADS, 0, st>>>(sorted, lo - 1, hi - 1, se_out);
+    if (lo < 1 || hi > n || hi < lo || !ws) return cudaErrorInvalidValue;
+    const int nleaf = std_count_leaves(lo - 1, hi - 1);
+    if (nleaf > STD_MAX_LEAVES) return cudaErrorInvalidValue;
+    unsigned int* done = reinterpret_cast<unsigned int*>(ws + STD_MAX_LEAVES + 1);
+    std_leaf_kernel<0><<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws, done, se_out);
+    std_leaf_kernel<1><<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws, done, se_out);
     return cudaGetLastError();
 }
 
@@ -341,7 +387,7 @@ cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se,
 #define BH_THREADS 1024
 __global__ void __launch_bounds__(BH_THREADS)
 bh_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64_t n, double* __restrict__ padj) {
-    __shared__ double cmin[BH_THREADS];
+    __shared__ double cmin[72];
     const int tid = threadIdx.x;
     const int64_t per = (n + BH_THREADS - 1) / BH_THREADS;
     const int64_t lo = (int64_t)tid * per, hi = (lo + per < n) ? lo + per : n;
@@ -350,15 +396,34 @@ bh_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64
         const double q = sp[i] * ((double)n / (double)(i + 1));
         mn = q < mn ? q : mn;
     }
-    cmin[tid] = mn;
+    // exclusive suffix minimum over the per-thread chunk minima (chunks strictly to the right)
+    const int lane = tid & 31, wid = tid >> 5;
+    double inc = mn;  // inclusive suffix min within the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_down_sync(0xffffffffu, inc, o);
+        if (lane + o < 32) inc = t < inc ? t : inc;
+    }
+    double excl = __shfl_down_sync(0xffffffffu, inc, 1);
+    if (lane == 31) excl = INFINITY;
+    if (lane == 0) cmin[wid] = inc;  // warp minimum
     __syncthreads();
-    // suffix minimum over chunk minima (exclusive: chunks strictly to the right)
-    if (tid == 0) {
-        double run = INFINITY;
-        for (int t = BH_THREADS - 1; t >= 0; --t) { const double v = cmin[t]; cmin[t] = run; run = v < run ? v : run; }
+    if (wid == 0) {
+        const double w = cmin[lane];
+        double winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_down_sync(0xffffffffu, winc, o);
+            if (lane + o < 32) winc = t < winc ? t : winc;
+        }
+        double wex = __shfl_down_sync(0xffffffffu, winc, 1);
+        if (lane == 31) wex = INFINITY;
+        cmin[32 + lane] = wex;  // min over warps strictly to the right
     }
     __syncthreads();
-    double run = cmin[tid];
+    {
+        const double wr = cmin[32 + wid];
+        excl = wr < excl ? wr : excl;
+    }
+    double run = excl;
     for (int64_t i = hi - 1; i >= lo; --i) {
         const double q = sp[i] * ((double)n / (double)(i + 1));
         run = q < run ? q : run;
