@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libreo_cuda.so")
+SO_PATH = os.environ.get("REO_CUDA_LIB") or os.path.join(HERE, "libreo_cuda.so")  # override: tuning variants
 
 REO_OK = 0
 REO_ERR_DIM = -1

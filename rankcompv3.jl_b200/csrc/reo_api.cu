@@ -368,7 +368,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     p.ntc = ntc;
     const int ntr = p.t1 - p.t0;
     if (ntr <= 0) return REO_OK;
-    const int want_items = 8 * 2 * D.num_sms;
+    const int want_items = 8 * 3 * D.num_sms;
     int njc = std::max(1, std::min(ntc, (want_items + ntr - 1) / ntr));
     p.jchunk = (ntc + njc - 1) / njc;
     p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;
@@ -671,6 +671,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     int rc = do_stage(h, data, dtype, r, c, ld, group_id, gnum, flags);
     if (rc) return rc;
     CK(cudaEventRecord(e_staged, D.st));
+    const auto wall1 = std::chrono::steady_clock::now();
     const ReoStaged& S = D.S;
     const int K = gnum == 2 ? 1 : gnum;
     CK(D.result.ensure((size_t)r * 15));
@@ -747,8 +748,10 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         it_host[k] = n_eval;
         st_local.iters_done = n_eval; st_local.converged = converged;
     }
+    const auto wall2 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(e_end, D.st));
     CK(cudaEventSynchronize(e_end));
+    const auto wall3 = std::chrono::steady_clock::now();
     float ms_stage = 0, ms_total = 0;
     cudaEventElapsedTime(&ms_stage, e_start, e_staged);
     cudaEventElapsedTime(&ms_total, e_start, e_end);
@@ -767,6 +770,13 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         st_local.ms_stats = ms_total - ms_stage - ms_pairs;
         st_local.pair_launches = h->pair_launches; st_local.kernel_launches = h->kernel_launches;
         st_local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+        if (getenv("REO_TIMING")) {
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+                return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[reo timing] stage %.3f loop %.3f endsync %.3f copyout %.3f | dev: stage %.3f pairs %.3f total %.3f\n",
+                    ms(wall0, wall1), ms(wall1, wall2), ms(wall2, wall3), ms(wall3, std::chrono::steady_clock::now()),
+                    (double)ms_stage, ms_pairs, (double)ms_total);
+        }
         *stats = st_local;
     }
     return REO_OK;

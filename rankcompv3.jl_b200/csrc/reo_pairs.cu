@@ -35,9 +35,16 @@
 
 #define PK_THREADS 256
 #define PK_WARPS (PK_THREADS / 32)
-#define PK_NS 4              // ring slots
+#ifndef PK_NS
+#define PK_NS 2              // ring slots
+#endif
+#ifndef PK_CTAS_PER_SM
+#define PK_CTAS_PER_SM 3    // resident CTAs per SM (<= 85 registers per thread)
+#endif
 #define PK_MAX_KW 4          // sample words per slot (upper bound)
-#define PK_SMEM_BUDGET (100 * 1024)
+#ifndef PK_SMEM_BUDGET
+#define PK_SMEM_BUDGET (70 * 1024)
+#endif
 #define PK_LUT_MAX_WORDS 4096   // lookup-table words (16 KB) above which the compare path is used
 
 #define PKF_FIRST_J 1
@@ -111,7 +118,7 @@ __device__ __forceinline__ uint32_t reo_class(int cnt, int n, int thr) {
 // NPT > 0: planes known at compile time (fully unrolled chain); NPT == 0: runtime p.NP.
 // LUT: classification through the shared-memory lookup tables (accumulators are shared-memory addresses).
 template <int NPT, bool LUT>
-__global__ void __launch_bounds__(PK_THREADS, 2) reo_pair_kernel(const ReoPairParams p) {
+__global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) reo_pair_kernel(const ReoPairParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int NP = NPT > 0 ? NPT : p.NP;
     const int KW = p.KW;
@@ -423,7 +430,8 @@ static int pair_kw(int NP, int W, int lut_words) {
     if (kw > PK_MAX_KW) kw = PK_MAX_KW;
     if (kw > W) kw = W;
     if (kw < 1) kw = 1;
-    return kw;
+    const int nsteps = (W + kw - 1) / kw;   // spread the words evenly over the steps of one column tile
+    return (W + nsteps - 1) / nsteps;
 }
 static size_t pair_smem_bytes(int NP, int KW, int lut_words) {
     return (size_t)PK_NS * 2 * KW * NP * REO_TILE * 4 + REO_TILE * 9 * 4 + PK_NS * sizeof(PkMeta) + PK_NS * 8 +
@@ -436,7 +444,7 @@ static cudaError_t launch_np_lut(const ReoPairParams& p, int lut_words, int num_
     cudaError_t e = cudaFuncSetAttribute(reo_pair_kernel<NPT, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nitems = (p.t1 - p.t0) * p.njchunks;
-    int grid = 2 * num_sms;
+    int grid = PK_CTAS_PER_SM * num_sms;
     if (grid > nitems) grid = nitems;
     if (grid < 1) return cudaSuccess;
     reo_pair_kernel<NPT, LUT><<<grid, PK_THREADS, smem, st>>>(p);
