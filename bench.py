@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_bulk_20kx200", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "torch"],
+                    help="N>1: all-gather by NCCL inside the library (default) or through torch.distributed")
     args = ap.parse_args()
     pkg = ge.load_package()
     if args.impl == "reference":
@@ -193,7 +195,10 @@ def main():
     if world > 1:
         from importlib import import_module
         dmod = import_module(pkg.__name__ + ".dist")
-        h.set_collective(rank, world, dmod.make_torch_allgather(rank, world))
+        if args.collective == "nccl":
+            dmod.init_nccl_in_library(h, rank, world)
+        else:
+            h.set_collective(rank, world, dmod.make_torch_allgather(rank, world))
 
     # inputs: pinned host copy (e2e) and an HBM-resident copy (value); column-major r x c Int64 = Julia's Matrix
     host = torch.from_numpy(np.ascontiguousarray(data.T)).pin_memory()     # [c, r] row-major == r x c column-major
@@ -283,7 +288,7 @@ def main():
                        "n_ref_initial": int(ref.sum()), "n_iter": 128, "n_conv": 5,
                        "evaluations": st_dev[-1]["iters_done"], "n_deg_per_evaluation": st_dev[-1]["n_deg"],
                        "l2": "flushed between timed steps (256 MB write); inputs are 32 MB",
-                       "sharding": f"gene-row tiles over {world} rank(s), NCCL all-gather of per-gene tables"},
+                       "sharding": f"gene-row tiles over {world} rank(s), all-gather of per-gene tables via {args.collective}"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(data.nbytes + gid.nbytes + ref.nbytes),
                     "d2h_bytes_per_step": int(r * 15 * 8 + 2 * r)},

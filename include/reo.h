@@ -80,8 +80,9 @@ typedef int (*reo_allgather_fn)(void* ctx, void* dev_buf, uint64_t bytes_per_ran
 
 int reo_version(void);
 
-/* ndev >= 1 devices driven by this (single) process; devs == NULL -> 0..ndev-1.
- * seed keys the tie coins.  Replaces nothing in the reference (it has no handle). */
+/* ndev >= 1 devices driven by this (single) process; devs == NULL -> 0..ndev-1.  With ndev > 1 gene-row
+ * tiles are sharded over the devices (one host thread each inside every call) and the per-gene tables are
+ * all-gathered with NCCL (ncclCommInitAll).  seed keys the tie coins.  The reference has no handle. */
 int reo_create(reo_handle_t* out, int ndev, const int* devs, uint64_t seed, uint32_t flags);
 int reo_destroy(reo_handle_t h);
 const char* reo_last_error(reo_handle_t h); /* h may be NULL: last create error */
@@ -90,12 +91,19 @@ const char* reo_last_error(reo_handle_t h); /* h may be NULL: last create error 
  * are sharded by rank and tables exchanged through `fn` (e.g. torch.distributed all_gather). */
 int reo_set_collective(reo_handle_t h, int rank, int world, reo_allgather_fn fn, void* ctx);
 
+/* One process per GPU with NCCL inside the library: rank 0 calls reo_comm_unique_id (128 bytes), every
+ * rank receives a copy over any host channel and calls reo_comm_init_rank.  Tables are then all-gathered
+ * with ncclAllGather on the handle's own stream (no host synchronisation, NVLink/NVSwitch transport). */
+int reo_comm_unique_id(void* out128);
+int reo_comm_init_rank(reo_handle_t h, int rank, int world, const void* id128);
+
 /* get_major_reo_lower_count(sample_size, pval_threshold), src:81-92.  Host arithmetic. */
 int reo_threshold(int sample_size, double pval_reo);
 
 /*
- * identify_degs, src:339-438: the whole path.  result: K x r x 15 doubles, k-major; per gene the
- * 15 columns of src:398/405/665 (pval padj n11 n12 n13 n21 n22 n23 n31 n32 n33 d1 d2 se z1).
+ * identify_degs, src:339-438: the whole path.  result: column-major r x 15 x K doubles (a Julia
+ * Array{Float64,3}(r, 15, K)): result[i + r*col + r*15*k], the 15 columns of src:398/405/665
+ * (pval padj n11 n12 n13 n21 n22 n23 n31 n32 n33 d1 d2 se z1).
  * updown: K x r (+1 "up", -1 "down", 0 "no change", src:426-429).  final_ref: K x r, the mask
  * used by the last evaluation (may be NULL).  iters_done: K ints (may be NULL).  stats may be NULL.
  */

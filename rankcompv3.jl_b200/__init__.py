@@ -8,5 +8,5 @@ sharding across one process per GPU).
 """
 from . import _lib, api, synth  # noqa: F401
 from .api import (DegResult, DeviceMatrix, McCullagh_test, Reo, get_major_reo_lower_count,  # noqa: F401
-                  identify_degs)
+                  identify_degs, nccl_unique_id)
 from .reoa import pseudobulk_group, reoa  # noqa: F401

@@ -24,7 +24,8 @@ REO_MAX_ITER_LOG = 256
 
 # every symbol include/reo.h declares
 SYMBOLS = [
-    "reo_version", "reo_create", "reo_destroy", "reo_last_error", "reo_set_collective", "reo_threshold",
+    "reo_version", "reo_create", "reo_destroy", "reo_last_error", "reo_set_collective", "reo_comm_unique_id",
+    "reo_comm_init_rank", "reo_threshold",
     "reo_identify_degs", "reo_stage", "reo_stage_info", "reo_pair_counts", "reo_tables", "reo_tables_delta",
     "reo_mccullagh", "reo_empirical_null", "reo_bh", "reo_sort_f64",
 ]
@@ -75,6 +76,10 @@ def load():
     L.reo_last_error.argtypes = [vp]
     L.reo_set_collective.restype = C.c_int
     L.reo_set_collective.argtypes = [vp, C.c_int, C.c_int, ALLGATHER_FN, vp]
+    L.reo_comm_unique_id.restype = C.c_int
+    L.reo_comm_unique_id.argtypes = [vp]
+    L.reo_comm_init_rank.restype = C.c_int
+    L.reo_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
     L.reo_threshold.restype = C.c_int
     L.reo_threshold.argtypes = [C.c_int, dbl]
     L.reo_identify_degs.restype = C.c_int

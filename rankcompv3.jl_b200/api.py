@@ -96,15 +96,19 @@ class DegResult:
 class Reo:
     """One libreo_cuda handle (one GPU)."""
 
-    def __init__(self, device: int = 0, seed: int = 0):
+    def __init__(self, device=0, seed: int = 0):
+        """device: one CUDA device index, or a list of indices (single process driving several GPUs: gene-row
+        tiles sharded over them, tables all-gathered with NCCL inside the library)."""
         self._lib = L.load()
         self._h = C.c_void_p()
-        devs = (C.c_int * 1)(int(device))
-        rc = self._lib.reo_create(C.byref(self._h), 1, devs, C.c_uint64(int(seed) & (2**64 - 1)), 0)
+        dl = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        devs = (C.c_int * len(dl))(*dl)
+        rc = self._lib.reo_create(C.byref(self._h), len(dl), devs, C.c_uint64(int(seed) & (2**64 - 1)), 0)
         if rc != 0:
             _raise(rc, (self._lib.reo_last_error(None) or b"").decode())
         self._cb = None
-        self.device = int(device)
+        self.device = dl[0]
+        self.devices = dl
 
     # -- plumbing ---------------------------------------------------------------------------
     def close(self):
@@ -144,6 +148,12 @@ class Reo:
             cb = L.ALLGATHER_FN(_tramp)
         self._cb = cb
         self._check(self._lib.reo_set_collective(self._h, int(rank), int(world), cb, None))
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        """One process per GPU: join the NCCL communicator identified by `unique_id` (128 bytes from
+        `nccl_unique_id()` on rank 0, shared over any host channel)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.reo_comm_init_rank(self._h, int(rank), int(world), buf))
 
     @staticmethod
     def _matrix_args(data):
@@ -249,6 +259,14 @@ class Reo:
         perm = np.zeros(len(x), dtype=np.int32)
         self._check(self._lib.reo_sort_f64(self._h, _ptr(x), len(x), _ptr(s), _ptr(perm)))
         return s, perm
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = L.load().reo_comm_unique_id(buf)
+    if rc != 0:
+        _raise(rc, (L.load().reo_last_error(None) or b"").decode())
+    return buf.raw
 
 
 # ---- module-level default handle ------------------------------------------------------------------

@@ -6,8 +6,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <mutex>
 #include <new>
 #include <string>
@@ -34,6 +38,38 @@ struct DBuf {  // grow-only device buffer
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+
+// NCCL is resolved at run time (dlopen) so that the single-GPU path has no link-time dependency and a
+// process that already carries a libnccl.so.2 (e.g. PyTorch's) shares it.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define REO_NCCL_SYM(field, name)                                              \
+        field = reinterpret_cast<decltype(field)>(dlsym(lib, name));           \
+        if (!field) { err = std::string("libnccl lacks ") + name; lib = nullptr; return false; }
+        REO_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        REO_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        REO_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+        REO_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        REO_NCCL_SYM(AllGather, "ncclAllGather")
+        REO_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef REO_NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
 
 }  // namespace
 
@@ -64,6 +100,7 @@ struct ReoDev {
     std::vector<cudaEvent_t> pev; // event pairs bracketing every pair-kernel launch of the current call
     int n_pev = 0;
     int64_t iota_r = -1;
+    ncclComm_t comm = nullptr;    // set by reo_comm_init_rank / multi-device reo_create
 };
 
 struct reo_handle_s {
@@ -76,6 +113,8 @@ struct reo_handle_s {
     // launch accounting of the current call
     int pair_launches = 0, kernel_launches = 0;
     int64_t compares = 0;
+    // single-process multi-GPU: one rank handle per device, driven by one host thread each
+    std::vector<reo_handle_s*> subs;
 };
 
 namespace {
@@ -405,10 +444,30 @@ int build_tables_full(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8
 
 int allgather_tables(reo_handle_t h, ReoDev& D) {
     if (h->world <= 1) return REO_OK;
-    if (!h->ag_fn) return fail(h, REO_ERR_COMM, "world > 1 but no all-gather callback set");
+    if (D.comm) {  // NCCL over NVLink, in place, ordered on the library's stream (no host synchronisation)
+        const size_t count = (size_t)(D.table_rows / h->world) * 9;
+        ncclResult_t nr = g_nccl.AllGather(D.table.p + (size_t)h->rank * count, D.table.p, count, ncclInt32, D.comm, D.st);
+        if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclAllGather: ") + g_nccl.GetErrorString(nr));
+        h->kernel_launches++;
+        return REO_OK;
+    }
+    if (!h->ag_fn) return fail(h, REO_ERR_COMM, "world > 1 but neither an NCCL communicator nor an all-gather callback is set");
     CK(cudaStreamSynchronize(D.st));
     const uint64_t bytes = (uint64_t)(D.table_rows / h->world) * 9 * sizeof(int32_t);
     if (h->ag_fn(h->ag_ctx, D.table.p, bytes) != 0) return fail(h, REO_ERR_COMM, "all-gather callback failed");
+    return REO_OK;
+}
+
+// run f(rank handle, rank) on every device of a multi-device handle, one host thread per device
+template <typename F>
+int run_multi(reo_handle_t parent, F f) {
+    const int n = (int)parent->subs.size();
+    std::vector<int> rcs(n, REO_OK);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i) th.emplace_back([&, i] { rcs[i] = f(parent->subs[i], i); });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rcs[i] != REO_OK) { parent->err = parent->subs[i]->err; return rcs[i]; }
     return REO_OK;
 }
 
@@ -425,45 +484,108 @@ const char* reo_last_error(reo_handle_t h) {
     return g_create_err.c_str();
 }
 
-int reo_create(reo_handle_t* out, int ndev, const int* devs, uint64_t seed, uint32_t /*flags*/) {
-    if (!out || ndev < 1) return fail(nullptr, REO_ERR_ARG, "reo_create: bad argument");
-    if (ndev > 1)
-        return fail(nullptr, REO_ERR_UNSUPPORTED,
-                    "single-process multi-GPU is not built yet: use one process per GPU with reo_set_collective");
+static int create_single(reo_handle_t* out, int dev, uint64_t seed) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count < 1) {
         cudaGetLastError();
         return fail(nullptr, REO_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
     }
+    if (dev < 0 || dev >= count) return fail(nullptr, REO_ERR_ARG, "reo_create: bad device index");
     reo_handle_s* h = new (std::nothrow) reo_handle_s();
     if (!h) return fail(nullptr, REO_ERR_OOM, "host allocation failed");
     h->seed = seed;
-    h->devs.resize(ndev);
-    for (int i = 0; i < ndev; ++i) {
-        ReoDev& D = h->devs[i];
-        D.dev = devs ? devs[i] : i;
-        if (D.dev < 0 || D.dev >= count) { delete h; return fail(nullptr, REO_ERR_ARG, "reo_create: bad device index"); }
-        if ((e = cudaSetDevice(D.dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking)) != cudaSuccess) {
-            delete h; cudaGetLastError();
-            return fail(nullptr, REO_ERR_CUDA, std::string("reo_create: ") + cudaGetErrorString(e));
-        }
-        cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, D.dev);
-        for (auto& ev : D.ev) cudaEventCreate(&ev);
-        if (cudaMallocHost((void**)&D.h_counts, 16 * sizeof(int32_t)) != cudaSuccess) {
-            delete h; cudaGetLastError();
-            return fail(nullptr, REO_ERR_OOM, "pinned allocation failed");
-        }
+    h->devs.resize(1);
+    ReoDev& D = h->devs[0];
+    D.dev = dev;
+    if ((e = cudaSetDevice(D.dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h; cudaGetLastError();
+        return fail(nullptr, REO_ERR_CUDA, std::string("reo_create: ") + cudaGetErrorString(e));
+    }
+    cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, D.dev);
+    for (auto& ev : D.ev) cudaEventCreate(&ev);
+    if (cudaMallocHost((void**)&D.h_counts, 16 * sizeof(int32_t)) != cudaSuccess) {
+        delete h; cudaGetLastError();
+        return fail(nullptr, REO_ERR_OOM, "pinned allocation failed");
     }
     *out = h;
     return REO_OK;
 }
 
+int reo_create(reo_handle_t* out, int ndev, const int* devs, uint64_t seed, uint32_t /*flags*/) {
+    if (!out || ndev < 1) return fail(nullptr, REO_ERR_ARG, "reo_create: bad argument");
+    if (ndev == 1) return create_single(out, devs ? devs[0] : 0, seed);
+    // single process, several GPUs (the Julia deployment): one rank handle per device, NCCL communicators
+    // from ncclCommInitAll, one host thread per device inside every call
+    {
+        std::lock_guard<std::mutex> g(g_nccl_mu);
+        if (!g_nccl.load()) return fail(nullptr, REO_ERR_COMM, g_nccl.err);
+    }
+    reo_handle_s* parent = new (std::nothrow) reo_handle_s();
+    if (!parent) return fail(nullptr, REO_ERR_OOM, "host allocation failed");
+    parent->seed = seed;
+    std::vector<int> devlist(ndev);
+    for (int i = 0; i < ndev; ++i) devlist[i] = devs ? devs[i] : i;
+    for (int i = 0; i < ndev; ++i) {
+        reo_handle_t sub = nullptr;
+        const int rc = create_single(&sub, devlist[i], seed);
+        if (rc != REO_OK) { for (auto* s : parent->subs) reo_destroy(s); delete parent; return rc; }
+        sub->rank = i; sub->world = ndev;
+        parent->subs.push_back(sub);
+    }
+    std::vector<ncclComm_t> comms(ndev);
+    const ncclResult_t nr = g_nccl.CommInitAll(comms.data(), ndev, devlist.data());
+    if (nr != ncclSuccess) {
+        const std::string m = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(nr);
+        for (auto* s : parent->subs) reo_destroy(s);
+        delete parent;
+        return fail(nullptr, REO_ERR_COMM, m);
+    }
+    for (int i = 0; i < ndev; ++i) parent->subs[i]->devs[0].comm = comms[i];
+    *out = parent;
+    return REO_OK;
+}
+
+/* 128-byte NCCL unique id for reo_comm_init_rank (rank 0 creates it, every rank receives a copy). */
+int reo_comm_unique_id(void* out128) {
+    if (!out128) return REO_ERR_ARG;
+    std::lock_guard<std::mutex> g(g_nccl_mu);
+    if (!g_nccl.load()) return fail(nullptr, REO_ERR_COMM, g_nccl.err);
+    ncclUniqueId id;
+    const ncclResult_t nr = g_nccl.GetUniqueId(&id);
+    if (nr != ncclSuccess) return fail(nullptr, REO_ERR_COMM, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(nr));
+    memcpy(out128, &id, sizeof(id));
+    return REO_OK;
+}
+
+/* One process per GPU: join an NCCL communicator; gene-row tiles are then sharded by rank and the tables
+ * all-gathered by NCCL on the library's own stream. */
+int reo_comm_init_rank(reo_handle_t h, int rank, int world, const void* id128) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world || !h->subs.empty())
+        return fail(h, REO_ERR_ARG, "reo_comm_init_rank: bad argument");
+    {
+        std::lock_guard<std::mutex> g(g_nccl_mu);
+        if (!g_nccl.load()) return fail(h, REO_ERR_COMM, g_nccl.err);
+    }
+    ReoDev& D = h->devs[0];
+    CK(cudaSetDevice(D.dev));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
+    const ncclResult_t nr = g_nccl.CommInitRank(&D.comm, world, id, rank);
+    if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nr));
+    h->rank = rank; h->world = world;
+    D.S.valid = false;
+    return REO_OK;
+}
+
 int reo_destroy(reo_handle_t h) {
     if (!h) return REO_OK;
+    for (auto* s : h->subs) reo_destroy(s);
     for (ReoDev& D : h->devs) {
         cudaSetDevice(D.dev);
         if (D.st) cudaStreamSynchronize(D.st);
+        if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
         D.raw.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
         D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
         D.changed_gene.release(); D.table.release(); D.perm.release(); D.counts.release(); D.fblist.release();
@@ -485,6 +607,7 @@ int reo_destroy(reo_handle_t h) {
 
 int reo_set_collective(reo_handle_t h, int rank, int world, reo_allgather_fn fn, void* ctx) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) return fail(h, REO_ERR_ARG, "reo_set_collective: handle already drives several devices");
     if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return fail(h, REO_ERR_ARG, "reo_set_collective: bad argument");
     h->rank = rank; h->world = world; h->ag_fn = fn; h->ag_ctx = ctx;
     h->devs[0].S.valid = false;  // table sizing depends on world
@@ -510,6 +633,10 @@ int reo_threshold(int n, double pval) {
 int reo_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, const int32_t* group_id,
               int32_t gnum, uint32_t flags) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) {
+        if (flags & REO_DATA_ON_DEVICE) return fail(h, REO_ERR_UNSUPPORTED, "REO_DATA_ON_DEVICE needs a single-device handle");
+        return run_multi(h, [&](reo_handle_t s, int) { return reo_stage(s, data, dtype, r, c, ld, group_id, gnum, flags); });
+    }
     h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0;
     h->devs[0].n_pev = 0;
     return do_stage(h, data, dtype, r, c, ld, group_id, gnum, flags);
@@ -517,6 +644,7 @@ int reo_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c,
 
 int reo_stage_info(reo_handle_t h, int32_t* rank_bits, int32_t* sample_words, int32_t* gene_tiles) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) return reo_stage_info(h->subs[0], rank_bits, sample_words, gene_tiles);
     const ReoStaged& S = h->devs[0].S;
     if (!S.valid) return fail(h, REO_ERR_STATE, "no staged matrix");
     if (rank_bits) *rank_bits = S.B;
@@ -528,6 +656,11 @@ int reo_stage_info(reo_handle_t h, int32_t* rank_bits, int32_t* sample_words, in
 int reo_pair_counts(reo_handle_t h, int32_t k, const int32_t* rows, int32_t nrows, const int32_t* cols, int32_t ncols,
                     int32_t* nre, int32_t* rest) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) {
+        const int rc = reo_pair_counts(h->subs[0], k, rows, nrows, cols, ncols, nre, rest);
+        if (rc) h->err = h->subs[0]->err;
+        return rc;
+    }
     ReoDev& D = h->devs[0];
     const ReoStaged& S = D.S;
     if (!S.valid) return fail(h, REO_ERR_STATE, "no staged matrix");
@@ -556,6 +689,16 @@ int reo_pair_counts(reo_handle_t h, int32_t k, const int32_t* rows, int32_t nrow
 int reo_tables_delta(reo_handle_t h, int32_t k, const int32_t* thresholds, double pval_reo, const uint8_t* mask_from,
                      const uint8_t* mask_to, int32_t* table) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) {
+        if (!table) return fail(h, REO_ERR_ARG, "reo_tables: bad argument");
+        const int64_t rr = h->subs[0]->devs[0].S.r;
+        std::vector<std::vector<int32_t>> scratch(h->subs.size());
+        return run_multi(h, [&](reo_handle_t s, int i) {
+            int32_t* out = table;
+            if (i > 0) { scratch[i].resize((size_t)std::max<int64_t>(rr, 1) * 9); out = scratch[i].data(); }
+            return reo_tables_delta(s, k, thresholds, pval_reo, mask_from, mask_to, out);
+        });
+    }
     ReoDev& D = h->devs[0];
     const ReoStaged& S = D.S;
     if (!S.valid) return fail(h, REO_ERR_STATE, "no staged matrix");
@@ -586,6 +729,7 @@ int reo_tables(reo_handle_t h, int32_t k, const int32_t* thresholds, double pval
 
 int reo_mccullagh(reo_handle_t h, const int64_t* tables, int64_t n, int32_t k, double* out) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_mccullagh(h->subs[0], tables, n, k, out); if (rc) h->err = h->subs[0]->err; return rc; }
     ReoDev& D = h->devs[0];
     if (!tables || !out || n < 1 || k < 2 || k > 9) return fail(h, REO_ERR_ARG, "reo_mccullagh: bad argument");
     CK(cudaSetDevice(D.dev));
@@ -600,6 +744,7 @@ int reo_mccullagh(reo_handle_t h, const int64_t* tables, int64_t n, int32_t k, d
 
 int reo_sort_f64(reo_handle_t h, const double* x, int64_t n, double* sorted, int32_t* perm) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_sort_f64(h->subs[0], x, n, sorted, perm); if (rc) h->err = h->subs[0]->err; return rc; }
     ReoDev& D = h->devs[0];
     if (!x || !sorted || n < 1) return fail(h, REO_ERR_ARG, "reo_sort_f64: bad argument");
     CK(cudaSetDevice(D.dev));
@@ -615,6 +760,7 @@ int reo_sort_f64(reo_handle_t h, const double* x, int64_t n, double* sorted, int
 
 int reo_empirical_null(reo_handle_t h, const double* delta1, int64_t n, double* pval, double* se) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_empirical_null(h->subs[0], delta1, n, pval, se); if (rc) h->err = h->subs[0]->err; return rc; }
     ReoDev& D = h->devs[0];
     if (!delta1 || !pval || n < 1) return fail(h, REO_ERR_ARG, "reo_empirical_null: bad argument");
     if (n <= 10) return fail(h, REO_ERR_BOUNDS, "BoundsError: r <= 10 (src:411)");
@@ -634,6 +780,7 @@ int reo_empirical_null(reo_handle_t h, const double* delta1, int64_t n, double* 
 
 int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_bh(h->subs[0], p, n, padj); if (rc) h->err = h->subs[0]->err; return rc; }
     ReoDev& D = h->devs[0];
     if (!p || !padj || n < 1) return fail(h, REO_ERR_ARG, "reo_bh: bad argument");
     CK(cudaSetDevice(D.dev));
@@ -658,6 +805,34 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
                       uint32_t flags, double* result, int8_t* updown, uint8_t* final_ref, int32_t* iters_done,
                       reo_stats* stats) {
     if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) {
+        if (flags & REO_DATA_ON_DEVICE) return fail(h, REO_ERR_UNSUPPORTED, "REO_DATA_ON_DEVICE needs a single-device handle");
+        if (!result || !updown || r < 1) return fail(h, REO_ERR_ARG, "reo_identify_degs: NULL argument");
+        const int K = gnum == 2 ? 1 : std::max(gnum, 1);
+        const size_t n = h->subs.size();
+        std::vector<std::vector<double>> res(n);
+        std::vector<std::vector<int8_t>> ud(n);
+        std::vector<reo_stats> sts(n);
+        const int rc = run_multi(h, [&](reo_handle_t s, int i) {
+            double* ro = result; int8_t* uo = updown;
+            if (i > 0) { res[i].resize((size_t)K * r * 15); ud[i].resize((size_t)K * r); ro = res[i].data(); uo = ud[i].data(); }
+            return reo_identify_degs(s, data, dtype, r, c, ld, group_id, gnum, thresholds, pval_reo, pval_deg, padj_deg,
+                                     ref_mask, n_iter, n_conv, flags, ro, uo, i == 0 ? final_ref : nullptr,
+                                     i == 0 ? iters_done : nullptr, &sts[i]);
+        });
+        if (rc == REO_OK && stats) {
+            *stats = sts[0];
+            for (size_t i = 1; i < n; ++i) {  // whole-job work; times are the slowest rank's
+                stats->compares += sts[i].compares;
+                stats->kernel_launches += sts[i].kernel_launches; stats->pair_launches += sts[i].pair_launches;
+                stats->ms_total = std::max(stats->ms_total, sts[i].ms_total);
+                stats->ms_pairs = std::max(stats->ms_pairs, sts[i].ms_pairs);
+                stats->ms_stage = std::max(stats->ms_stage, sts[i].ms_stage);
+                stats->ms_wall = std::max(stats->ms_wall, sts[i].ms_wall);
+            }
+        }
+        return rc;
+    }
     if (!data || !group_id || !ref_mask || !result || !updown) return fail(h, REO_ERR_ARG, "reo_identify_degs: NULL argument");
     if (gnum < 2) return fail(h, REO_ERR_DIM, "Only 1 level in 'group', at least 2 levels!");
     if (r <= 10) return fail(h, REO_ERR_BOUNDS, "BoundsError: r <= 10 (src:411)");

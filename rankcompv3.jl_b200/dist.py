@@ -50,3 +50,13 @@ def allgather_rows_cpu(local_rows, rank: int, world: int, n_tiles: int, group=No
     full = torch.zeros((world * tpr * TILE, 9), dtype=torch.int32)
     dist.all_gather_into_tensor(full, mine, group=group)
     return full.numpy()
+
+
+def init_nccl_in_library(handle, rank: int, world: int, group=None):
+    """One process per GPU: create the library's own NCCL communicator (tables are then all-gathered on the
+    library's stream with no host round trip).  The 128-byte unique id travels over torch.distributed."""
+    import torch.distributed as dist
+    from . import api
+    box = [api.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    handle.comm_init(rank, world, box[0])

@@ -272,3 +272,23 @@ def test_full_size_properties_config2(reo, pkg, oracle, coracle):
     called = out.updown[0] != 0
     assert (called & is_de).sum() > 0.7 * is_de.sum() and (called & ~is_de).sum() < 0.1 * called.sum() + 50
     assert out.stats["kernel_launches"] > 0 and out.stats["compares"] > 0
+
+
+# ---- several GPUs in one process (the Julia deployment shape) ------------------------------------
+def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    data, group = small_case(31, 700, 40, 45)
+    levels, gid = oracle.group_levels(group)
+    ref = np.arange(700) % 5 == 0
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    want = coracle.identify_degs(data, gid, 2, thr, 1.0, 0.05, ref, 128, 5, seed=7)
+    ndev = min(torch.cuda.device_count(), 4)
+    with pkg.Reo(list(range(ndev)), seed=pkg.synth.TIE_SEED) as h:
+        out = h.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5)
+        check_full(out, want)
+        h.stage(data, gid, 2)
+        mask = np.arange(700) % 3 != 0
+        tab, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)
+        assert np.array_equal(h.tables(0, mask, thresholds=thr), tab)
