@@ -250,7 +250,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
              int32_t gnum, uint32_t flags) {
     ReoDev& D = h->devs[0];
     ReoStaged& S = D.S;
-    S.valid = false;
+    S.valid = false; S.flt = false;
     const size_t es = dtype_size(dtype);
     if (!data || !group_id || es == 0 || r < 1 || c < 1 || ld < r) return fail(h, REO_ERR_ARG, "reo_stage: bad argument");
     if (gnum < 2) return fail(h, REO_ERR_DIM, "Only 1 level in 'group', at least 2 levels!");
@@ -327,10 +327,17 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     }
     CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
-    if (D.h_counts[0])
-        return fail(h, REO_ERR_UNSUPPORTED,
-                    "non-integral expression values: the 0.1 tie band of is_greater (src:72) is not rank-"
-                    "compressible; the float path is not built yet");
+    if (D.h_counts[0]) {
+        // non-integral values: the 0.1 tie band of is_greater (src:72) is not transitive, so ranks cannot be
+        // used -- stage the raw values as FP64 and let the pair kernel compare them directly
+        if (dtype != REO_F64 && dtype != REO_F32) return fail(h, REO_ERR_ARG, "non-integral values in an integer matrix");
+        S.flt = true; S.B = 0; S.NP = 1;
+        CK(D.planes.ensure((size_t)S.NT * S.tile_stride()));
+        S.planes = D.planes.p;
+        CKL(reo_launch_fstage(dev_data, dtype, r, dev_ld, D.sample_of_slot.p, S.NT, S.W, (uint32_t)h->seed,
+                              (uint32_t)(h->seed >> 32), S.planes, D.st));
+        h->kernel_launches++;
+    } else {
     const int nfb = D.h_counts[1];
     if (nfb > 0) {
         int64_t rp2 = 1;
@@ -357,6 +364,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     CKL(reo_launch_bitplanes(D.ranks.p, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
                             (uint32_t)(h->seed >> 32), S.planes, D.st));
     h->kernel_launches++;
+    }
     // identity column list for "all genes are references" (cached while r is unchanged)
     if (D.iota_r != r) {
         std::vector<int32_t> iota(rpad, -1);
@@ -392,7 +400,8 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     const uint32_t* colp = S.planes;
     if (!all_genes) {
         CK(D.panel.ensure((size_t)ntc * S.tile_stride()));
-        CKL(reo_launch_gather_panel(S.planes, S.W, S.NP, col_gene_dev, ntc, D.panel.p, D.st));
+        if (S.flt) CKL(reo_launch_gather_panel_flt(S.planes, S.W, col_gene_dev, ntc, D.panel.p, D.st));
+        else CKL(reo_launch_gather_panel(S.planes, S.W, S.NP, col_gene_dev, ntc, D.panel.p, D.st));
         h->kernel_launches++;
         colp = D.panel.p;
     }
@@ -413,6 +422,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;
     p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
     p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;
+    p.flt = S.flt ? 1 : 0;
     CK(cudaMemsetAsync(D.counter.p, 0, sizeof(unsigned int), D.st));
     if ((size_t)(2 * D.n_pev + 2) > D.pev.size()) {
         cudaEvent_t a, b;

@@ -16,6 +16,8 @@
 #define REO_TILE 64            // genes per tile
 #define REO_MAX_BITS 16        // rank bits (u16 ranks)
 #define REO_MAX_PLANES (REO_MAX_BITS + 1)
+// float path: one operand word = 64 coin words + 32 samples x 64 genes FP64
+#define REO_FLT_OPWORDS (REO_TILE + 32 * REO_TILE * 2)
 
 // ---- tie coin: must match oracle/reo_oracle.{py,c} bit for bit --------------------------------
 __host__ __device__ __forceinline__ uint32_t reo_mix32(uint32_t x) {
@@ -37,7 +39,8 @@ struct ReoStaged {
     int W = 0;         // sample words (all levels)
     int B = 0;         // rank bits
     int NP = 0;        // planes = B + 1
-    uint32_t* planes = nullptr;      // [NT][W][NP][64]
+    uint32_t* planes = nullptr;      // [NT][W][NP][64]; float path: [NT][W][REO_FLT_OPWORDS]
+    bool flt = false;                // non-integral input: raw FP64 values instead of rank planes
     std::vector<int> lev_word0;      // first word of each level
     std::vector<int> lev_words;      // words of each level
     std::vector<int> lev_n;          // real samples of each level
@@ -45,8 +48,8 @@ struct ReoStaged {
     int mixed_word = -1;             // index of that word, -1 if none
     int mixed_rem[2] = {0, 0};       // level 0 occupies bits [0, rem0), level 1 bits [rem0, rem0 + rem1)
     bool valid = false;
-    size_t word_stride() const { return (size_t)NP * REO_TILE; }
-    size_t tile_stride() const { return (size_t)W * NP * REO_TILE; }
+    size_t word_stride() const { return flt ? (size_t)REO_FLT_OPWORDS : (size_t)NP * REO_TILE; }
+    size_t tile_stride() const { return (size_t)W * word_stride(); }
 };
 
 // ---- pair kernel parameters ---------------------------------------------------------------------
@@ -70,6 +73,7 @@ struct ReoPairParams {
     uint32_t maskA, maskB;
     int KW;                      // sample words per pipeline slot (set by the launcher)
     int use_lut, lutSZA, lutSZB; // class lookup tables in shared memory (set by the launcher)
+    int flt;                     // 1: planes hold raw FP64 values (REO_FLT_OPWORDS words per operand word)
     unsigned int one;            // == 1 (see mad_acc in reo_pairs.cu)
 };
 
@@ -96,6 +100,11 @@ cudaError_t reo_launch_bitplanes(const uint16_t* ranks, int64_t rpad, int64_t r,
                                  cudaStream_t st);
 cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const int32_t* col_gene, int ntc,
                                     uint32_t* panel, cudaStream_t st);
+
+cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* sample_of_slot, int NT,
+                              int W, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes, cudaStream_t st);
+cudaError_t reo_launch_gather_panel_flt(const uint32_t* planes, int W, const int32_t* col_gene, int ntc, uint32_t* panel,
+                                        cudaStream_t st);
 
 // statistics (reo_stats.cu)
 cudaError_t reo_launch_mccullagh_tables(const int32_t* table, int64_t r, double* result /*col-major r x 15*/,

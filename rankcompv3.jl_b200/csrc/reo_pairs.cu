@@ -117,12 +117,16 @@ __device__ __forceinline__ uint32_t reo_class(int cnt, int n, int thr) {
 
 // NPT > 0: planes known at compile time (fully unrolled chain); NPT == 0: runtime p.NP.
 // LUT: classification through the shared-memory lookup tables (accumulators are shared-memory addresses).
-template <int NPT, bool LUT>
-__global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) reo_pair_kernel(const ReoPairParams p) {
+// FLT: non-integral expression values: the 0.1 tie band of is_greater (src:72) is not
+//      transitive, so ranks cannot be used; an operand word is [64 coin words][32 samples][64 genes] FP64
+//      and the 32 "is greater" bits of a word come from FP64 compares on the raw values instead of the
+//      LOP3 chain.  Everything around it (ring, classification, tables) is shared with the rank path.
+template <int NPT, bool LUT, bool FLT>
+__global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair_kernel(const ReoPairParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int NP = NPT > 0 ? NPT : p.NP;
     const int KW = p.KW;
-    const int op_words = NP * REO_TILE;                 // words of one operand tile for one sample word
+    const int op_words = FLT ? REO_FLT_OPWORDS : NP * REO_TILE;   // words of one operand tile for one sample word
     const uint32_t op_bytes = (uint32_t)op_words * 4u;
     const int stage_words = 2 * KW * op_words;          // rows then columns
     uint32_t* stages = reinterpret_cast<uint32_t*>(smem_raw);
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) reo_pair_kernel(co
     __syncthreads();
 
     const int nchunks = (p.W + KW - 1) / KW;
-    const size_t word_stride = (size_t)p.NP * REO_TILE;
+    const size_t word_stride = FLT ? (size_t)REO_FLT_OPWORDS : (size_t)p.NP * REO_TILE;
     const size_t tile_stride = (size_t)p.W * word_stride;
     const int nitems = (p.t1 - p.t0) * p.njchunks;
 
@@ -323,47 +327,89 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) reo_pair_kernel(co
             const uint32_t* xr = srow + kk * op_words + ty * 4;
             const uint32_t* yc = scol + kk * op_words + tx * 4;
             uint32_t bor[4][4];
-            {
+            if (FLT) {
+                // raw-value path: per sample d = x - y; "greater" iff d >= 0.1, tie iff -0.1 < d < 0.1
+                // (== abs(x - y) < 0.1 ? coin : x > y, src:72-76), 32 samples -> two bit masks per pair
+                uint32_t gtm[4][4], lem[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) { gtm[a][b] = 0u; lem[a][b] = 0u; }
+                const double* xd = reinterpret_cast<const double*>(srow + kk * op_words + REO_TILE) + ty * 4;
+                const double* yd = reinterpret_cast<const double*>(scol + kk * op_words + REO_TILE) + tx * 4;
+#pragma unroll 2
+                for (int sidx = 0; sidx < 32; ++sidx) {
+                    const double2 x01 = *reinterpret_cast<const double2*>(xd + sidx * REO_TILE);
+                    const double2 x23 = *reinterpret_cast<const double2*>(xd + sidx * REO_TILE + 2);
+                    const double2 y01 = *reinterpret_cast<const double2*>(yd + sidx * REO_TILE);
+                    const double2 y23 = *reinterpret_cast<const double2*>(yd + sidx * REO_TILE + 2);
+                    const double x[4] = {x01.x, x01.y, x23.x, x23.y};
+                    const double y[4] = {y01.x, y01.y, y23.x, y23.y};
+                    const uint32_t bit = 1u << sidx;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const double d = x[a] - y[b];
+                            if (d >= 0.1) gtm[a][b] |= bit;
+                            if (d > -0.1) lem[a][b] |= bit;
+                        }
+                }
                 const uint4 xv = *reinterpret_cast<const uint4*>(xr);
                 const uint4 yv = *reinterpret_cast<const uint4*>(yc);
-                const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+                const uint32_t xc[4] = {xv.x, xv.y, xv.z, xv.w};
+                const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) bor[a][b] = lop3_xor3(x[a], y[b], om);
-            }
-            if (!uniform) {   // rare: flip the coin seed of the pairs whose orientation differs from pair (0,0)
-                uint32_t ob = obits;
-                asm volatile("" : "+r"(ob));   // keep the mask arithmetic inside this branch
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) bor[a][b] ^= (0u - (((ob >> (a * 4 + b)) ^ ob) & 1u));
-            }
-            if (NPT > 0) {
-#pragma unroll
-                for (int pl = 1; pl < (NPT > 0 ? NPT : 1); ++pl) {
-                    const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
-                    const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
-                    const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
-                }
+                    for (int b = 0; b < 4; ++b) {
+                        uint32_t coin = xc[a] ^ yw[b] ^ om;
+                        if (!uniform) coin ^= (0u - (((obits >> (a * 4 + b)) ^ obits) & 1u));
+                        bor[a][b] = gtm[a][b] | (lem[a][b] & ~gtm[a][b] & coin);
+                    }
             } else {
-#pragma unroll 2
-                for (int pl = 1; pl < NP; ++pl) {
-                    const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
-                    const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
+            {
+                    const uint4 xv = *reinterpret_cast<const uint4*>(xr);
+                    const uint4 yv = *reinterpret_cast<const uint4*>(yc);
                     const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
                     const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                        for (int b = 0; b < 4; ++b) bor[a][b] = lop3_xor3(x[a], y[b], om);
+                }
+                if (!uniform) {   // rare: flip the coin seed of the pairs whose orientation differs from pair (0,0)
+                    uint32_t ob = obits;
+                    asm volatile("" : "+r"(ob));   // keep the mask arithmetic inside this branch
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) bor[a][b] ^= (0u - (((ob >> (a * 4 + b)) ^ ob) & 1u));
+                }
+                if (NPT > 0) {
+#pragma unroll
+                    for (int pl = 1; pl < (NPT > 0 ? NPT : 1); ++pl) {
+                        const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
+                        const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
+                        const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
+                        const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                    }
+                } else {
+#pragma unroll 2
+                    for (int pl = 1; pl < NP; ++pl) {
+                        const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
+                        const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
+                        const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
+                        const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                    }
                 }
             }
             if (boundary && p.mixed) {
@@ -438,16 +484,16 @@ static size_t pair_smem_bytes(int NP, int KW, int lut_words) {
            sizeof(PkProd) + PK_NS * 4 + (size_t)lut_words * 4 + 16;
 }
 
-template <int NPT, bool LUT>
+template <int NPT, bool LUT, bool FLT = false>
 static cudaError_t launch_np_lut(const ReoPairParams& p, int lut_words, int num_sms, cudaStream_t st) {
-    const size_t smem = pair_smem_bytes(p.NP, p.KW, lut_words);
-    cudaError_t e = cudaFuncSetAttribute(reo_pair_kernel<NPT, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = pair_smem_bytes(FLT ? REO_FLT_OPWORDS / REO_TILE : p.NP, p.KW, lut_words);
+    cudaError_t e = cudaFuncSetAttribute(reo_pair_kernel<NPT, LUT, FLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nitems = (p.t1 - p.t0) * p.njchunks;
     int grid = PK_CTAS_PER_SM * num_sms;
     if (grid > nitems) grid = nitems;
     if (grid < 1) return cudaSuccess;
-    reo_pair_kernel<NPT, LUT><<<grid, PK_THREADS, smem, st>>>(p);
+    reo_pair_kernel<NPT, LUT, FLT><<<grid, PK_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -463,6 +509,15 @@ static cudaError_t launch_np(ReoPairParams p, int num_sms, cudaStream_t st) {
 
 cudaError_t reo_launch_pairs(const ReoPairParams& p, int num_sms, cudaStream_t st) {
     if (p.t1 <= p.t0 || p.ntc <= 0) return cudaSuccess;
+    if (p.flt) {   // raw FP64 values: operand word = REO_FLT_OPWORDS words
+        ReoPairParams q = p;
+        pair_lut_sizes(q, &q.lutSZA, &q.lutSZB, &q.use_lut);
+        const int lut_words = q.use_lut ? 2 * q.lutSZA + 6 * q.lutSZB : 0;
+        q.KW = pair_kw(REO_FLT_OPWORDS / REO_TILE, q.W, lut_words);
+        q.one = 1u;
+        return q.use_lut ? launch_np_lut<0, true, true>(q, lut_words, num_sms, st)
+                         : launch_np_lut<0, false, true>(q, lut_words, num_sms, st);
+    }
     switch (p.NP) {
 #define CASE_NP(n) case n: return launch_np<n>(p, num_sms, st);
         CASE_NP(2) CASE_NP(3) CASE_NP(4) CASE_NP(5) CASE_NP(6) CASE_NP(7) CASE_NP(8) CASE_NP(9) CASE_NP(10)
@@ -482,6 +537,30 @@ __global__ void pair_counts_small_kernel(const uint32_t* __restrict__ planes, in
     if (idx >= nrows * ncols) return;
     const int gi = rows[idx / ncols], gj = cols[idx % ncols];
     const uint32_t om = gi < gj ? 0xffffffffu : 0u;
+    if (NP == 0) {   // float path: [64 coin words][32][64] FP64 per (tile, word)
+        const size_t ws = REO_FLT_OPWORDS, ts = (size_t)W * ws;
+        int a = 0, b = 0;
+        for (int k = 0; k < W; ++k) {
+            const int w = word_order[k];
+            const uint32_t* bi = planes + (size_t)(gi >> 6) * ts + (size_t)w * ws;
+            const uint32_t* bj = planes + (size_t)(gj >> 6) * ts + (size_t)w * ws;
+            const double* xi = reinterpret_cast<const double*>(bi + REO_TILE) + (gi & 63);
+            const double* yj = reinterpret_cast<const double*>(bj + REO_TILE) + (gj & 63);
+            const uint32_t coin = bi[gi & 63] ^ bj[gj & 63] ^ om;
+            uint32_t bor = 0u;
+            for (int sidx = 0; sidx < 32; ++sidx) {
+                const double d = xi[sidx * REO_TILE] - yj[sidx * REO_TILE];
+                const uint32_t gt = d >= 0.1, tie = (d > -0.1) && !(d >= 0.1);
+                bor |= (gt | (tie & (coin >> sidx))) << sidx;
+            }
+            if (k == WA && mixed) { a += __popc(bor & maskA); b += __popc(bor & maskB); }
+            else if (k < WA) a += __popc(bor);
+            else b += __popc(bor);
+        }
+        nre[idx] = a - (int)(om & (uint32_t)padA);
+        rest[idx] = b - (int)(om & (uint32_t)padB);
+        return;
+    }
     const size_t ws = (size_t)NP * REO_TILE, ts = (size_t)W * ws;
     const uint32_t* pi = planes + (size_t)(gi >> 6) * ts + (gi & 63);
     const uint32_t* pj = planes + (size_t)(gj >> 6) * ts + (gj & 63);
@@ -508,7 +587,7 @@ cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word
                                          int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB, cudaStream_t st) {
     const int n = nrows * ncols;
     if (n <= 0) return cudaSuccess;
-    pair_counts_small_kernel<<<(n + 127) / 128, 128, 0, st>>>(S.planes, S.W, S.NP, word_order, WA, rows, nrows, cols,
+    pair_counts_small_kernel<<<(n + 127) / 128, 128, 0, st>>>(S.planes, S.W, S.flt ? 0 : S.NP, word_order, WA, rows, nrows, cols,
                                                               ncols, nre, rest, padA, padB, mixed, maskA, maskB);
     return cudaGetLastError();
 }

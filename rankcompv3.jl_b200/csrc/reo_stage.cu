@@ -322,3 +322,65 @@ cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const
     gather_panel_kernel<<<grid, 256, 0, st>>>(planes, W, NP, col_gene, panel);
     return cudaGetLastError();
 }
+
+
+// ---- float path staging ----------------------------------------------------------
+// planes[t][w] = [64 coin words][32 samples][64 genes] FP64 raw values (pad slots / pad genes = 0.0)
+template <typename T>
+__global__ void __launch_bounds__(256)
+fstage_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* __restrict__ sample_of_slot, int W,
+              uint32_t seed_lo, uint32_t seed_hi, uint32_t* __restrict__ planes) {
+    const int t = blockIdx.x, w = blockIdx.y, l = threadIdx.x, y = threadIdx.y;
+    const int64_t g = (int64_t)t * REO_TILE + l;
+    uint32_t* base = planes + ((size_t)t * W + w) * REO_FLT_OPWORDS;
+    double* vals = reinterpret_cast<double*>(base + REO_TILE);
+    for (int sidx = y; sidx < 32; sidx += 4) {
+        const int so = sample_of_slot[(int64_t)w * 32 + sidx];
+        double v = 0.0;
+        if (so >= 0 && g < r) v = (double)data[(int64_t)so * ld + g];
+        vals[sidx * REO_TILE + l] = v;
+    }
+    if (y == 0) {
+        uint32_t coin = 0u;
+        if (g < r) {
+            for (int sidx = 0; sidx < 32; ++sidx) {
+                const int so = sample_of_slot[(int64_t)w * 32 + sidx];
+                if (so >= 0) coin |= reo_coin_u(seed_lo, seed_hi, (uint32_t)g, (uint32_t)so) << sidx;
+            }
+        }
+        base[l] = coin;
+    }
+}
+
+cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* sample_of_slot, int NT,
+                              int W, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes, cudaStream_t st) {
+    dim3 grid(NT, W), block(REO_TILE, 4);
+    switch (dtype) {
+        case REO_F64: fstage_kernel<double><<<grid, block, 0, st>>>((const double*)data, r, ld, sample_of_slot, W, seed_lo, seed_hi, planes); break;
+        case REO_F32: fstage_kernel<float><<<grid, block, 0, st>>>((const float*)data, r, ld, sample_of_slot, W, seed_lo, seed_hi, planes); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// float panel gather: panel[tc][w] = [coin words of the listed genes][32][64] values of the listed genes
+__global__ void __launch_bounds__(256)
+gather_panel_flt_kernel(const uint32_t* __restrict__ planes, int W, const int32_t* __restrict__ col_gene,
+                        uint32_t* __restrict__ panel) {
+    const int tc = blockIdx.x, w = blockIdx.y, l = threadIdx.x & 63, y = threadIdx.x >> 6;
+    const int g = col_gene[tc * REO_TILE + l];
+    const uint32_t* src = g >= 0 ? planes + ((size_t)(g >> 6) * W + w) * REO_FLT_OPWORDS : nullptr;
+    uint32_t* dst = panel + ((size_t)tc * W + w) * REO_FLT_OPWORDS;
+    if (y == 0) dst[l] = src ? src[g & 63] : 0u;
+    const double* sv = src ? reinterpret_cast<const double*>(src + REO_TILE) : nullptr;
+    double* dv = reinterpret_cast<double*>(dst + REO_TILE);
+    for (int sidx = y; sidx < 32; sidx += 4) dv[sidx * REO_TILE + l] = sv ? sv[sidx * REO_TILE + (g & 63)] : 0.0;
+}
+
+cudaError_t reo_launch_gather_panel_flt(const uint32_t* planes, int W, const int32_t* col_gene, int ntc, uint32_t* panel,
+                                        cudaStream_t st) {
+    if (ntc <= 0) return cudaSuccess;
+    dim3 grid(ntc, W);
+    gather_panel_flt_kernel<<<grid, 256, 0, st>>>(planes, W, col_gene, panel);
+    return cudaGetLastError();
+}

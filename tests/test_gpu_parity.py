@@ -73,11 +73,50 @@ def test_wide_value_range_uses_sort_fallback(reo, oracle):
     assert np.array_equal(nre, want[0]) and np.array_equal(rest, want[1])
 
 
-def test_non_integral_input_is_refused_loudly(reo, oracle):
-    data, group = small_case(13, 50, 6, 6)
+def float_case(seed, r, n1, n2, n3=0):
+    """log-scale expression with many values inside the 0.1 tie band (non-transitive ties, src:72)."""
+    data, group = small_case(seed, r, n1, n2, scale=1, n3=n3)
+    rng = np.random.default_rng(seed)
+    x = np.log1p(data) + rng.normal(0, 0.04, data.shape)
+    x[rng.random(data.shape) < 0.1] = 0.0
+    return np.round(x, 3), group
+
+
+@pytest.mark.parametrize("seed,r,n1,n2,n3,dtype", [(1, 90, 7, 9, 0, np.float64), (2, 150, 40, 33, 0, np.float64),
+                                                   (3, 70, 12, 30, 9, np.float64), (4, 100, 20, 20, 0, np.float32)])
+def test_float_path_pair_counts_and_tables(reo, oracle, coracle, seed, r, n1, n2, n3, dtype):
+    """non-integral input goes through the raw-value FP64 compare path, bit-exact vs the oracle."""
+    data, group = float_case(seed, r, n1, n2, n3)
+    data = data.astype(dtype)
     levels, gid = oracle.group_levels(group)
-    with pytest.raises(NotImplementedError):
-        reo.stage(data.astype(np.float64) + 0.05, gid, 2)
+    gnum = len(levels)
+    info = reo.stage(data, gid, gnum)
+    assert info["rank_bits"] == 0  # float mode: no rank planes
+    rows = np.arange(0, r, 2)
+    cols = np.arange(1, r, 3)
+    want = oracle.greater_counts(data.astype(np.float64), gid, gnum, rows, cols, seed=7)
+    for k in range(gnum if gnum > 2 else 1):
+        nre, rest = reo.pair_counts(k, rows, cols)
+        assert np.array_equal(nre, want[k]) and np.array_equal(rest, want.sum(axis=0) - want[k])
+    thr = coracle.thresholds_for(gid, gnum, 0.01)
+    mask = np.random.default_rng(seed).random(r) < 0.5
+    for k in range(gnum if gnum > 2 else 1):
+        tab, _ = coracle.block_tables(data.astype(np.float64), gid, gnum, thr, np.nonzero(mask)[0], seed=7, k=k)
+        assert np.array_equal(reo.tables(k, mask, thresholds=thr), tab)
+    # all genes as references + incremental update
+    full = np.ones(r, bool)
+    tab, _ = coracle.block_tables(data.astype(np.float64), gid, gnum, thr, np.arange(r), seed=7)
+    assert np.array_equal(reo.tables(0, mask, thresholds=thr, mask_to=full), tab)
+
+
+def test_float_path_identify_degs(reo, oracle, coracle):
+    data, group = float_case(8, 400, 25, 30)
+    levels, gid = oracle.group_levels(group)
+    ref = np.arange(400) % 4 == 0
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    want = coracle.identify_degs(data, gid, 2, thr, 1.0, 0.05, ref, 128, 5, seed=7)
+    out = reo.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5)
+    check_full(out, want)
 
 
 # ---- K2 tables ----------------------------------------------------------------------------------
