@@ -146,6 +146,22 @@ int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj);
 /* ascending stable sort of doubles on the device (used by the two above); perm may be NULL. */
 int reo_sort_f64(reo_handle_t h, const double* x, int64_t n, double* sorted, int32_t* perm);
 
+/* ---- the steps right before the path, HBM-bound streaming kernels ------- */
+
+/* pseudobulk_group, src:56-67 / 608-612: out[:, p] = sum of data[:, s] over s in cell_list[cell_ptr[p] .. cell_ptr[p+1])
+ * in that order (the random shuffle + partition of src:62 stays a host decision).  out: r x nprofiles column-major,
+ * Int64 for integer input, Float64 for float input.  out_host may be NULL; *out_dev (may be NULL) receives a
+ * handle-owned device pointer valid until the next reo_pseudobulk -- pass it to reo_identify_degs with
+ * REO_DATA_ON_DEVICE so the pseudo-bulk matrix never leaves HBM. */
+int reo_pseudobulk(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, const int32_t* cell_ptr,
+                   const int32_t* cell_list, int32_t nprofiles, uint32_t flags, void* out_host, void** out_dev);
+/* src:618, 626: per_cell[s] = #{i : data[i,s] > 0}, per_gene[i] = #{s : data[i,s] > 0}. */
+int reo_detect_counts(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, uint32_t flags,
+                      int32_t* per_cell, int32_t* per_gene);
+/* src:624-628: out = data[gene_list, cell_list] (r2 x c2 column-major, same dtype); out_host / out_dev as above. */
+int reo_subset(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, const int32_t* gene_list,
+               int64_t r2, const int32_t* cell_list, int64_t c2, uint32_t flags, void* out_host, void** out_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ SYMBOLS = [
     "reo_version", "reo_create", "reo_destroy", "reo_last_error", "reo_set_collective", "reo_comm_unique_id",
     "reo_comm_init_rank", "reo_threshold",
     "reo_identify_degs", "reo_stage", "reo_stage_info", "reo_pair_counts", "reo_tables", "reo_tables_delta",
-    "reo_mccullagh", "reo_empirical_null", "reo_bh", "reo_sort_f64",
+    "reo_mccullagh", "reo_empirical_null", "reo_bh", "reo_sort_f64", "reo_pseudobulk", "reo_detect_counts", "reo_subset",
 ]
 
 
@@ -103,5 +103,11 @@ def load():
     L.reo_bh.argtypes = [vp, vp, i64, vp]
     L.reo_sort_f64.restype = C.c_int
     L.reo_sort_f64.argtypes = [vp, vp, i64, vp, vp]
+    L.reo_pseudobulk.restype = C.c_int
+    L.reo_pseudobulk.argtypes = [vp, vp, C.c_int, i64, i64, i64, vp, vp, i32, u32, vp, C.POINTER(vp)]
+    L.reo_detect_counts.restype = C.c_int
+    L.reo_detect_counts.argtypes = [vp, vp, C.c_int, i64, i64, i64, u32, vp, vp]
+    L.reo_subset.restype = C.c_int
+    L.reo_subset.argtypes = [vp, vp, C.c_int, i64, i64, i64, vp, i64, vp, i64, u32, vp, C.POINTER(vp)]
     _lib = L
     return L

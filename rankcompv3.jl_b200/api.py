@@ -253,6 +253,47 @@ class Reo:
         self._check(self._lib.reo_bh(self._h, _ptr(p), len(p), _ptr(q)))
         return q
 
+    # -- the steps right before the path ------------------------------------------
+    def pseudobulk(self, data, profiles, to_host=True):
+        """profiles: list of cell-index arrays (one per pseudo-bulk profile, summed in the given order), src:56-67.
+        Returns (host matrix r x P or None, DeviceMatrix of the result kept in HBM)."""
+        p, dt, r, c, ld, flags, keep = self._matrix_args(data)
+        ptr = np.zeros(len(profiles) + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(x) for x in profiles])
+        cells = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.int32) for x in profiles])
+                                     if len(profiles) else np.zeros(0, np.int32), dtype=np.int32)
+        is_int = dt in (L.REO_I64, L.REO_I32)
+        out = np.empty((len(profiles), r), dtype=np.int64 if is_int else np.float64) if to_host else None
+        dev = C.c_void_p()
+        self._check(self._lib.reo_pseudobulk(self._h, p, dt, r, c, ld, _ptr(ptr), _ptr(cells), len(profiles), flags,
+                                             _ptr(out), C.byref(dev)))
+        del keep
+        dm = DeviceMatrix(dev.value, L.REO_I64 if is_int else L.REO_F64, r, len(profiles), r, keepalive=self)
+        return (out.T if out is not None else None), dm
+
+    def detect_counts(self, data):
+        """src:618, 626 -> (detected genes per cell [c], detecting cells per gene [r])."""
+        p, dt, r, c, ld, flags, keep = self._matrix_args(data)
+        per_cell = np.zeros(c, dtype=np.int32)
+        per_gene = np.zeros(r, dtype=np.int32)
+        self._check(self._lib.reo_detect_counts(self._h, p, dt, r, c, ld, flags, _ptr(per_cell), _ptr(per_gene)))
+        del keep
+        return per_cell, per_gene
+
+    def subset(self, data, genes, cells, to_host=True):
+        """data[genes, cells] (src:624-628) -> (host matrix or None, DeviceMatrix)."""
+        p, dt, r, c, ld, flags, keep = self._matrix_args(data)
+        genes = np.ascontiguousarray(genes, dtype=np.int32)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        npdt = {v: k for k, v in _DT.items()}[dt]
+        out = np.empty((len(cells), len(genes)), dtype=npdt) if to_host else None
+        dev = C.c_void_p()
+        self._check(self._lib.reo_subset(self._h, p, dt, r, c, ld, _ptr(genes), len(genes), _ptr(cells), len(cells), flags,
+                                         _ptr(out), C.byref(dev)))
+        del keep
+        dm = DeviceMatrix(dev.value, dt, len(genes), len(cells), len(genes), keepalive=self)
+        return (out.T if out is not None else None), dm
+
     def sort(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         s = np.zeros_like(x)

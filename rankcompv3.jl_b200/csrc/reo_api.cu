@@ -79,7 +79,7 @@ struct ReoDev {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8] = {};
     ReoStaged S;
-    DBuf<uint8_t> raw;
+    DBuf<uint8_t> raw, raw2, pb, sub;
     DBuf<uint16_t> ranks;
     DBuf<uint32_t> planes, panel;
     DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, counts,
@@ -596,7 +596,7 @@ int reo_destroy(reo_handle_t h) {
         cudaSetDevice(D.dev);
         if (D.st) cudaStreamSynchronize(D.st);
         if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
-        D.raw.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
+        D.raw.release(); D.raw2.release(); D.pb.release(); D.sub.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
         D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
         D.changed_gene.release(); D.table.release(); D.perm.release(); D.counts.release(); D.fblist.release();
         D.small_i.release(); D.changed_sign.release(); D.updown.release(); D.mask_a.release(); D.mask_b.release();
@@ -806,6 +806,89 @@ int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj) {
     }
     CK(cudaMemcpyAsync(padj, d_q, n * 8, cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+// matrix on the device for the pre-processing entry points: the caller's device pointer, or a copy in raw2
+static int prep_input(reo_handle_t h, ReoDev& D, const void* data, int dtype, int64_t r, int64_t c, int64_t ld,
+                      uint32_t flags, const uint8_t** dev, int64_t* dev_ld) {
+    const size_t es = dtype_size(dtype);
+    if (!data || es == 0 || r < 1 || c < 1 || ld < r) return fail(h, REO_ERR_ARG, "bad matrix argument");
+    CK(cudaSetDevice(D.dev));
+    if (flags & REO_DATA_ON_DEVICE) { *dev = (const uint8_t*)data; *dev_ld = ld; return REO_OK; }
+    CK(D.raw2.ensure((size_t)r * c * es));
+    CK(cudaMemcpy2DAsync(D.raw2.p, (size_t)r * es, data, (size_t)ld * es, (size_t)r * es, (size_t)c, cudaMemcpyHostToDevice, D.st));
+    *dev = D.raw2.p; *dev_ld = r;
+    return REO_OK;
+}
+
+/* pseudobulk_group, src:56-67 / 608-612: out[:, p] = sum over the cells cell_list[cell_ptr[p] .. cell_ptr[p+1]) (in that
+ * order).  out is r x nprofiles column-major, Int64 for integer input and Float64 for float input; out_host and/or
+ * out_dev (handle-owned, valid until the next reo_pseudobulk) may be NULL. */
+int reo_pseudobulk(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, const int32_t* cell_ptr,
+                   const int32_t* cell_list, int32_t nprofiles, uint32_t flags, void* out_host, void** out_dev) {
+    if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_pseudobulk(h->subs[0], data, dtype, r, c, ld, cell_ptr, cell_list, nprofiles, flags, out_host, out_dev); if (rc) h->err = h->subs[0]->err; return rc; }
+    ReoDev& D = h->devs[0];
+    if (!cell_ptr || !cell_list || nprofiles < 1) return fail(h, REO_ERR_ARG, "reo_pseudobulk: bad argument");
+    const int32_t ncells = cell_ptr[nprofiles];
+    if (cell_ptr[0] != 0 || ncells < 0) return fail(h, REO_ERR_ARG, "reo_pseudobulk: bad cell_ptr");
+    for (int p = 0; p < nprofiles; ++p) if (cell_ptr[p + 1] < cell_ptr[p]) return fail(h, REO_ERR_ARG, "reo_pseudobulk: bad cell_ptr");
+    for (int32_t k = 0; k < ncells; ++k) if (cell_list[k] < 0 || cell_list[k] >= c) return fail(h, REO_ERR_DIM, "reo_pseudobulk: cell index out of range");
+    const uint8_t* dev; int64_t dld;
+    int rc = prep_input(h, D, data, dtype, r, c, ld, flags, &dev, &dld);
+    if (rc) return rc;
+    CK(D.small_i.ensure((size_t)nprofiles + 1 + (size_t)std::max(ncells, 1)));
+    CK(cudaMemcpyAsync(D.small_i.p, cell_ptr, ((size_t)nprofiles + 1) * 4, cudaMemcpyHostToDevice, D.st));
+    if (ncells > 0) CK(cudaMemcpyAsync(D.small_i.p + nprofiles + 1, cell_list, (size_t)ncells * 4, cudaMemcpyHostToDevice, D.st));
+    CK(D.pb.ensure((size_t)r * nprofiles * 8));
+    CKL(reo_launch_pseudobulk(dev, dtype, r, dld, D.small_i.p, D.small_i.p + nprofiles + 1, nprofiles, D.pb.p, D.st));
+    if (out_host) CK(cudaMemcpyAsync(out_host, D.pb.p, (size_t)r * nprofiles * 8, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    if (out_dev) *out_dev = D.pb.p;
+    return REO_OK;
+}
+
+/* src:618, 626: per_cell[s] = #{ i : data[i,s] > 0 } (c ints), per_gene[i] = #{ s : data[i,s] > 0 } (r ints). */
+int reo_detect_counts(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, uint32_t flags,
+                      int32_t* per_cell, int32_t* per_gene) {
+    if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_detect_counts(h->subs[0], data, dtype, r, c, ld, flags, per_cell, per_gene); if (rc) h->err = h->subs[0]->err; return rc; }
+    ReoDev& D = h->devs[0];
+    if (!per_cell || !per_gene) return fail(h, REO_ERR_ARG, "reo_detect_counts: bad argument");
+    const uint8_t* dev; int64_t dld;
+    int rc = prep_input(h, D, data, dtype, r, c, ld, flags, &dev, &dld);
+    if (rc) return rc;
+    CK(D.small_i.ensure((size_t)r + c));
+    CK(cudaMemsetAsync(D.small_i.p, 0, ((size_t)r + c) * 4, D.st));
+    CKL(reo_launch_detect_counts(dev, dtype, r, c, dld, D.small_i.p, D.small_i.p + c, D.st));
+    CK(cudaMemcpyAsync(per_cell, D.small_i.p, (size_t)c * 4, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaMemcpyAsync(per_gene, D.small_i.p + c, (size_t)r * 4, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    return REO_OK;
+}
+
+/* src:624-628: out = data[gene_list, cell_list], r2 x c2 column-major, same dtype.  out_host / out_dev as above. */
+int reo_subset(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld, const int32_t* gene_list,
+               int64_t r2, const int32_t* cell_list, int64_t c2, uint32_t flags, void* out_host, void** out_dev) {
+    if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_subset(h->subs[0], data, dtype, r, c, ld, gene_list, r2, cell_list, c2, flags, out_host, out_dev); if (rc) h->err = h->subs[0]->err; return rc; }
+    ReoDev& D = h->devs[0];
+    if (!gene_list || !cell_list || r2 < 1 || c2 < 1) return fail(h, REO_ERR_ARG, "reo_subset: bad argument");
+    for (int64_t i = 0; i < r2; ++i) if (gene_list[i] < 0 || gene_list[i] >= r) return fail(h, REO_ERR_DIM, "reo_subset: gene index out of range");
+    for (int64_t s = 0; s < c2; ++s) if (cell_list[s] < 0 || cell_list[s] >= c) return fail(h, REO_ERR_DIM, "reo_subset: cell index out of range");
+    const uint8_t* dev; int64_t dld;
+    int rc = prep_input(h, D, data, dtype, r, c, ld, flags, &dev, &dld);
+    if (rc) return rc;
+    const size_t es = dtype_size(dtype);
+    CK(D.small_i.ensure((size_t)r2 + c2));
+    CK(cudaMemcpyAsync(D.small_i.p, gene_list, (size_t)r2 * 4, cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemcpyAsync(D.small_i.p + r2, cell_list, (size_t)c2 * 4, cudaMemcpyHostToDevice, D.st));
+    CK(D.sub.ensure((size_t)r2 * c2 * es));
+    CKL(reo_launch_subset(dev, dtype, dld, D.small_i.p, r2, D.small_i.p + r2, c2, D.sub.p, D.st));
+    if (out_host) CK(cudaMemcpyAsync(out_host, D.sub.p, (size_t)r2 * c2 * es, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    if (out_dev) *out_dev = D.sub.p;
     return REO_OK;
 }
 

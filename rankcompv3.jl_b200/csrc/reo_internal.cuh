@@ -106,6 +106,14 @@ cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld
 cudaError_t reo_launch_gather_panel_flt(const uint32_t* planes, int W, const int32_t* col_gene, int ntc, uint32_t* panel,
                                         cudaStream_t st);
 
+// pre-processing next to the path (reo_prep.cu)
+cudaError_t reo_launch_pseudobulk(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* cell_ptr,
+                                  const int32_t* cell_list, int nprofiles, void* out, cudaStream_t st);
+cudaError_t reo_launch_detect_counts(const void* data, int dtype, int64_t r, int64_t c, int64_t ld, int32_t* per_cell,
+                                     int32_t* per_gene, cudaStream_t st);
+cudaError_t reo_launch_subset(const void* data, int dtype, int64_t ld, const int32_t* gene_list, int64_t r2,
+                              const int32_t* cell_list, int64_t c2, void* out, cudaStream_t st);
+
 // statistics (reo_stats.cu)
 cudaError_t reo_launch_mccullagh_tables(const int32_t* table, int64_t r, double* result /*col-major r x 15*/,
                                         cudaStream_t st);

@@ -78,28 +78,36 @@ def reoa(fn_expr: str = "fn_expr.txt", fn_metadata: str = "fn_metadata.txt", *, 
         raise ValueError(f"ArgumentError: {fn_expr} expression matrix contains non-numeric (Number) profiles.")
     gene_names = expr["Name"].astype(str).to_numpy()
     rng = np.random.default_rng(seed)
-    if n_pseudo > 0:  # src:608-612
-        blocks, names, groups = [], [], []
+    h = handle or api.default_handle(seed)
+    if n_pseudo > 0:  # src:608-612; the shuffle/partition is decided here, the row sums run on the device
+        all_cols = list(meta["Name"])
+        full = expr[all_cols].to_numpy()
+        col_index = {n: i for i, n in enumerate(all_cols)}
+        profiles, names, groups = [], [], []
         for g in g_name:
-            cols = list(meta["Name"][meta["Group"] == g])
-            pb = pseudobulk_group(expr[cols].to_numpy(), n_pseudo, rng)
-            blocks.append(pb)
-            names += [f"{g}_x{i + 1}" for i in range(pb.shape[1])]
-            groups += [g] * pb.shape[1]
-        mat = np.concatenate(blocks, axis=1)
+            cols = np.array([col_index[n] for n in meta["Name"][meta["Group"] == g]], dtype=np.int32)
+            cp = int(np.ceil(len(cols) / n_pseudo))  # src:60
+            perm = cols[rng.permutation(len(cols))]
+            parts = [perm[i:i + cp] for i in range(0, len(perm), cp)]
+            names += [f"{g}_x{i + 1}" for i in range(len(parts))]
+            groups += [g] * len(parts)
+            profiles += parts
+        mat, _ = h.pseudobulk(full, profiles)
         meta_group = pd.DataFrame({"Name": names, "Group": groups})
     else:  # src:614-615: every column after the first, matched to meta rows by position
         mat = expr.iloc[:, 1:].to_numpy()
         names = list(expr.columns[1:])
         meta_group = meta.copy()
     # src:618-628
-    s_inds = (mat > 0).sum(axis=0) > min_profiles
+    per_cell, _ = h.detect_counts(mat)            # device: detected genes per profile
+    s_inds = per_cell > min_profiles
     if (~s_inds).any():
         dropped = {names[i] for i in np.nonzero(~s_inds)[0]}
         meta_group = meta_group[~meta_group.iloc[:, 0].isin(dropped)]
     mat = mat[:, s_inds]
     names = [n for n, keep in zip(names, s_inds) if keep]
-    inds = (mat > 0).sum(axis=1) > min_features
+    _, per_gene = h.detect_counts(mat)            # device: detecting profiles per gene
+    inds = per_gene > min_features
     gene_names = gene_names[inds]
     mat = mat[inds, :]
     print(f"INFO: size after filtering lowly expressed genes and profiles and pseudo-bulk sampling, {mat.shape}")
@@ -121,7 +129,7 @@ def reoa(fn_expr: str = "fn_expr.txt", fn_metadata: str = "fn_metadata.txt", *, 
     ref_gene_vec = np.array([g in ref_gene for g in gene_names], dtype=bool)
     group = list(meta_group["Group"])
     res = api.identify_degs(mat, group, gene_names, pval_reo, pval_deg, padj_deg, ref_gene_vec, n_iter, n_conv,
-                            handle=handle or api.default_handle(seed))
+                            handle=h)
     # src:663-683
     K = (res.shape[1] - 1) // 16
     cols = {}

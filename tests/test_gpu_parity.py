@@ -331,3 +331,69 @@ def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
         mask = np.arange(700) % 3 != 0
         tab, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)
         assert np.array_equal(h.tables(0, mask, thresholds=thr), tab)
+
+
+# ---- next to the path: pseudo-bulk, detection filters, subsetting ---------------
+@pytest.mark.parametrize("dtype", [np.int64, np.int32, np.float64, np.float32])
+def test_pseudobulk_detect_subset(reo, pkg, dtype):
+    rng = np.random.default_rng(3)
+    r, c, n_pseudo = 333, 207, 10
+    x = rng.poisson(0.6, size=(r, c)).astype(dtype)
+    if np.issubdtype(dtype, np.floating):
+        x = (x * 1.25).astype(dtype)
+    # src:60-63: shuffle, partition into chunks of ceil(c/n_pseudo)
+    perm = rng.permutation(c)
+    cp = -(-c // n_pseudo)
+    profiles = [perm[i:i + cp] for i in range(0, c, cp)]
+    host, dm = reo.pseudobulk(x, profiles)
+    want = np.stack([x[:, p].astype(np.float64 if np.issubdtype(dtype, np.floating) else np.int64).sum(axis=1)
+                     for p in profiles], axis=1)
+    if np.issubdtype(dtype, np.floating):
+        assert np.allclose(host, want, rtol=1e-13)
+        seq = np.stack([np.add.reduce(x[:, p].astype(np.float64), axis=1) for p in profiles], axis=1)
+        assert host.shape == seq.shape
+    else:
+        assert np.array_equal(host, want)
+    assert dm.r == r and dm.c == len(profiles)
+    per_cell, per_gene = reo.detect_counts(x)
+    assert np.array_equal(per_cell, (x > 0).sum(axis=0)) and np.array_equal(per_gene, (x > 0).sum(axis=1))
+    genes = np.nonzero(per_gene > 40)[0]
+    cells = np.nonzero(per_cell > 120)[0]
+    sub, dms = reo.subset(x, genes, cells)
+    assert np.array_equal(sub, x[np.ix_(genes, cells)])
+    # chained on the device: pseudo-bulk output -> identify_degs without leaving HBM
+    if dtype == np.int64:
+        gid = np.array([0] * (len(profiles) // 2) + [1] * (len(profiles) - len(profiles) // 2), dtype=np.int32)
+        ref = np.arange(r) % 3 == 0
+        a = reo.identify_degs(dm, gid, 2, ref, 0.01, 1.0, 0.05, 16, 2)
+        b = reo.identify_degs(host, gid, 2, ref, 0.01, 1.0, 0.05, 16, 2)
+        assert np.array_equal(a.result, b.result) and np.array_equal(a.updown, b.updown)
+
+
+def test_reoa_driver_end_to_end(reo, pkg, tmp_path):
+    """reoa() mirror (src:536-685): files in, TSVs out, same calls as a direct identify_degs."""
+    import pandas as pd
+    data, group, is_de = pkg.synth.bulk(600, 9, 11, seed=4)
+    data[5, :] = 0  # an all-zero gene row is dropped by the > min_features filter (src:626)
+    cols = [f"S{i}" for i in range(20)]
+    expr = pd.DataFrame(data, columns=cols)
+    expr.insert(0, "gene_name", [f"G{i}" for i in range(600)])
+    expr.to_csv(tmp_path / "fn_expr.txt", sep="\t", index=False)
+    pd.DataFrame({"sample_name": cols, "group": group}).to_csv(tmp_path / "fn_meta.txt", sep="\t", index=False)
+    out = pkg.reoa("fn_expr.txt", "fn_meta.txt", use_hk_genes="no", ref_gene_max=150, work_dir=str(tmp_path), seed=3,
+                   handle=reo)
+    assert list(out.columns) == ["gene_name", "group1_vs_group2"] and len(out) == 599
+    assert set(out["group1_vs_group2"]) <= {"up", "down", "no change"}
+    for f in ("fn_expr_group1_group2_result.tsv", "fn_expr_df_expr.tsv", "fn_expr_df_meta.tsv", "fn_expr_gene_up_down.tsv"):
+        assert (tmp_path / f).exists(), f
+    res = pd.read_csv(tmp_path / "fn_expr_group1_group2_result.tsv", sep="\t")
+    assert list(res.columns) == ["genename"] + pkg.api.HEADER and len(res) == 599
+    called = out["group1_vs_group2"].to_numpy() != "no change"
+    keep = np.ones(600, bool); keep[5] = False
+    assert (called & is_de[keep]).sum() > 0.5 * called.sum()
+    # pseudo-bulk mode (src:608-612): 20 cells -> 2 x 3 profiles
+    out2 = pkg.reoa("fn_expr.txt", "fn_meta.txt", use_hk_genes="no", ref_gene_max=150, work_dir=str(tmp_path), seed=3,
+                    n_pseudo=3, handle=reo, write_files=False)
+    assert len(out2) <= 600 and list(out2.columns)[1] == "group1_vs_group2"
+    with pytest.raises(ValueError, match="ArgumentError"):
+        pkg.reoa("nope.txt", "fn_meta.txt", work_dir=str(tmp_path), handle=reo)
