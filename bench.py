@@ -48,10 +48,16 @@ WORKLOADS = {
 }
 
 
-def make_workload(pkg, name):
+def make_workload(pkg, name, device=None):
+    """Returns (column-major r x c Int64 numpy matrix, group ids, reference mask).  Single-cell shapes are
+    generated on the GPU when one is given (same model, seconds instead of minutes) and copied back."""
     kind, r, n1, n2, n_ref, _ = WORKLOADS[name]
     if kind == "bulk":
         data, group, is_de = pkg.synth.bulk(r, n1, n2)
+    elif device is not None:
+        t, group, is_de = pkg.synth.scrna_torch(r, n1, n2, device=device)
+        data = t.cpu().numpy().T          # [c, r] row-major -> F-ordered r x c view
+        del t
     else:
         data, group, is_de = pkg.synth.scrna(r, n1, n2)
     ref = pkg.synth.reference_mask(is_de, n_ref) if n_ref > 0 else np.ones(r, dtype=bool)
@@ -189,7 +195,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     args.warmup = max(args.warmup, 3)
 
-    data, gid, ref = make_workload(pkg, args.workload)
+    data, gid, ref = make_workload(pkg, args.workload, device=f"cuda:{local}")
     r, c = data.shape
     h = pkg.Reo(local, seed=pkg.synth.TIE_SEED)
     if world > 1:

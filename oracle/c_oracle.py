@@ -41,6 +41,10 @@ def lib():
         L.reo_oracle_block_tables.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                               C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_int64,
                                               C.c_void_p, C.c_int64, C.c_void_p]
+        L.reo_oracle_block_tables_idx.restype = C.c_int64
+        L.reo_oracle_block_tables_idx.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
+                                                  C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                                  C.c_void_p, C.c_int64, C.c_void_p]
         L.reo_oracle_empirical_null.restype = C.c_double
         L.reo_oracle_empirical_null.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.reo_oracle_bh.restype = None
@@ -111,6 +115,22 @@ def block_tables(data, gid, gnum, thr, cols, seed=0, k=0, i0=0, i1=None):
     n = lib().reo_oracle_block_tables(_p(d), r, c, r, _p(gid), int(gnum), _p(thr_cm), int(seed), int(k), i0, i1,
                                       _p(cols), len(cols), _p(tab))
     return tab, int(n)
+
+
+def block_tables_idx(sub, gidx, gid, gnum, thr, rows_local, cols_local, seed=0, k=0):
+    """Tables of sub-matrix rows against sub-matrix columns; local row i is global gene gidx[i] (ascending)."""
+    d = _colmajor_f64(sub)
+    r, c = d.shape
+    gid = np.ascontiguousarray(gid, dtype=np.int32)
+    gidx = np.ascontiguousarray(gidx, dtype=np.int32)
+    assert np.all(np.diff(gidx) > 0)
+    thr_cm = np.asfortranarray(np.asarray(thr, dtype=np.int32))
+    rows = np.ascontiguousarray(rows_local, dtype=np.int32)
+    cols = np.ascontiguousarray(cols_local, dtype=np.int32)
+    tab = np.zeros((len(rows), 9), dtype=np.int32)
+    lib().reo_oracle_block_tables_idx(_p(d), r, c, r, _p(gid), int(gnum), _p(thr_cm), int(seed), int(k), _p(gidx),
+                                      _p(rows), len(rows), _p(cols), len(cols), _p(tab))
+    return tab
 
 
 def empirical_null(d1):

@@ -209,6 +209,20 @@ static inline int classify(int64_t nre, int64_t not_, int64_t n1, int64_t n2, in
     return 3 * (ic - 1) + it;
 }
 
+static void make_ctx_idx(reo_ctx* x, const double* data, int64_t r, int64_t c, int64_t ld, const int32_t* gid,
+                         int gnum, uint64_t seed, const int32_t* gidx, double** xt_out, uint8_t** ut_out) {
+    double* xt = (double*)malloc(sizeof(double) * (size_t)r * (size_t)c);
+    uint8_t* ut = (uint8_t*)malloc((size_t)r * (size_t)c);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < r; ++i)
+        for (int64_t s = 0; s < c; ++s) {
+            xt[i * c + s] = data[i + ld * s];
+            ut[i * c + s] = (uint8_t)reo_oracle_u(seed, (uint32_t)(gidx ? gidx[i] : i), (uint32_t)s);
+        }
+    x->r = r; x->c = c; x->gnum = gnum; x->xt = xt; x->ut = ut; x->gid = gid;
+    *xt_out = xt; *ut_out = ut;
+}
+
 static void make_ctx(reo_ctx* x, const double* data, int64_t r, int64_t c, int64_t ld, const int32_t* gid,
                      int gnum, uint64_t seed, double** xt_out, uint8_t** ut_out) {
     double* xt = (double*)malloc(sizeof(double) * (size_t)r * (size_t)c);
@@ -278,6 +292,39 @@ int64_t reo_oracle_block_tables(const double* data, int64_t r, int64_t c, int64_
     }
     free(xt); free(ut);
     return (i1 - i0) * ncols * c;
+}
+
+/*
+ * Same as reo_oracle_block_tables for a SUB-MATRIX of a larger problem: local row i is global gene gidx[i]
+ * (coins u(gidx[i], s) and the orientation [gidx[i] < gidx[j]] use the global indices; gidx must be ascending).
+ * Lets tests check row blocks of matrices too large to hand to the oracle whole.
+ */
+int64_t reo_oracle_block_tables_idx(const double* data, int64_t r, int64_t c, int64_t ld, const int32_t* gid, int gnum,
+                                    const int32_t* thr, uint64_t seed, int k_sel, const int32_t* gidx,
+                                    const int32_t* rows, int64_t nrows, const int32_t* cols, int64_t ncols,
+                                    int32_t* table) {
+    reo_ctx x; double* xt; uint8_t* ut;
+    make_ctx_idx(&x, data, r, c, ld, gid, gnum, seed, gidx, &xt, &ut);
+    int64_t n1 = 0;
+    for (int64_t s = 0; s < c; ++s) n1 += (gid[s] == k_sel);
+    int64_t n2 = c - n1;
+    memset(table, 0, sizeof(int32_t) * 9 * (size_t)nrows);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t a = 0; a < nrows; ++a) {
+        int64_t nre[64];
+        const int64_t i = rows[a];
+        int32_t* t = table + a * 9;
+        for (int64_t jj = 0; jj < ncols; ++jj) {
+            const int64_t j = cols[jj];
+            if (i == j) continue;
+            pair_counts(&x, i, j, nre);   /* local order == global order because gidx ascends */
+            int64_t tot = 0;
+            for (int g = 0; g < gnum; ++g) tot += nre[g];
+            t[classify(nre[k_sel], tot - nre[k_sel], n1, n2, thr[0 + 2 * k_sel], thr[1 + 2 * k_sel]) - 1] += 1;
+        }
+    }
+    free(xt); free(ut);
+    return nrows * ncols * c;
 }
 
 /* ---------------------------------------------------------------- empirical null + BH */

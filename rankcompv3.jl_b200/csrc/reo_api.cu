@@ -82,7 +82,7 @@ struct ReoDev {
     DBuf<uint8_t> raw, raw2, pb, sub;
     DBuf<uint16_t> ranks;
     DBuf<uint32_t> planes, panel;
-    DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, counts,
+    DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, perm2, counts,
         fblist, small_i;
     DBuf<int8_t> changed_sign, updown;
     DBuf<uint8_t> mask_a, mask_b;
@@ -598,7 +598,7 @@ int reo_destroy(reo_handle_t h) {
         if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
         D.raw.release(); D.raw2.release(); D.pb.release(); D.sub.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
         D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
-        D.changed_gene.release(); D.table.release(); D.perm.release(); D.counts.release(); D.fblist.release();
+        D.changed_gene.release(); D.table.release(); D.perm.release(); D.perm2.release(); D.counts.release(); D.fblist.release();
         D.small_i.release(); D.changed_sign.release(); D.updown.release(); D.mask_a.release(); D.mask_b.release();
         D.result.release(); D.sorted.release(); D.sorted_p.release(); D.se.release(); D.small_d.release();
         D.counter.release(); D.flags.release(); D.fb_keys.release(); D.fb_rank.release(); D.small_ll.release();
@@ -943,7 +943,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     const ReoStaged& S = D.S;
     const int K = gnum == 2 ? 1 : gnum;
     CK(D.result.ensure((size_t)r * 15));
-    CK(D.sorted.ensure(r)); CK(D.sorted_p.ensure(r)); CK(D.perm.ensure(r)); CK(D.se.ensure(1)); CK(D.updown.ensure(r));
+    CK(D.sorted.ensure(r)); CK(D.sorted_p.ensure(r)); CK(D.perm.ensure(r)); CK(D.perm2.ensure(r)); CK(D.se.ensure(1)); CK(D.updown.ensure(r));
     if ((rc = ensure_std_ws(h, D))) return rc;
     reo_stats st_local;
     memset(&st_local, 0, sizeof(st_local));
@@ -974,16 +974,16 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             // src:402-406
             CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
             // src:409-412
-            CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, nullptr, D.sortws, D.st));
+            CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, D.perm.p, D.sortws, D.st));
             CKL(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, D.std_ws.p, D.st));
             CKL(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));
-            // src:413
-            CKL(reo_launch_sort_f64(D.result.p, r, D.sorted_p.p, D.perm.p, D.sortws, D.st));
-            CKL(reo_launch_bh(D.sorted_p.p, D.perm.p, r, D.result.p + r, nullptr, D.st));
+            // src:413: the ascending order of p follows from the sorted d1 (p decreases with |d1|): no second sort
+            CKL(reo_launch_p_order(D.sorted.p, D.perm.p, r, D.result.p, D.sorted_p.p, D.perm2.p, D.st));
+            CKL(reo_launch_bh(D.sorted_p.p, D.perm2.p, r, D.result.p + r, nullptr, D.st));
             // src:417
             CKL(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));
             CKL(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
-            h->kernel_launches += 10;
+            h->kernel_launches += 10;  // mccullagh, sort x2, std x2, pvals, p_order, bh, inds, diff
             CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
             CK(cudaStreamSynchronize(D.st));
             const int n_ref = D.h_counts[0], n_inds = D.h_counts[1], n_chg = D.h_counts[2];

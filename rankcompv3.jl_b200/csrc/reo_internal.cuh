@@ -127,6 +127,8 @@ cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int3
                                 cudaStream_t st);
 cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* leaf_ws, cudaStream_t st);
 cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se, double* pval, cudaStream_t st);
+cudaError_t reo_launch_p_order(const double* sorted, const int32_t* perm1, int64_t n, const double* pval,
+                               double* sorted_p, int32_t* perm2, cudaStream_t st);
 cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* ws,
                           cudaStream_t st);
 // inds = !(p<=pd && q<=qd) (src:417)

@@ -41,7 +41,9 @@
 #ifndef PK_CTAS_PER_SM
 #define PK_CTAS_PER_SM 3    // resident CTAs per SM (<= 85 registers per thread)
 #endif
-#define PK_MAX_KW 4          // sample words per slot (upper bound)
+#ifndef PK_MAX_KW
+#define PK_MAX_KW 8          // sample words per slot (upper bound)
+#endif
 #ifndef PK_SMEM_BUDGET
 #define PK_SMEM_BUDGET (70 * 1024)
 #endif
@@ -53,7 +55,7 @@
 #define PKF_TERM 8
 
 struct PkMeta { int ti, J, w0, nw, flags, pad0, pad1, pad2; };
-struct PkProd { int count, step, nsteps, ti, jbeg, done, pad0, pad1; };   // producer state (shared memory)
+struct PkProd { int count, step, nsteps, ti, J, ch, done, pad1; };   // producer state (shared memory)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -193,15 +195,17 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
                 pst->done = 1; pst->count = pr_count + 1;
                 return;
             }
-            pst->ti = p.t0 + item / p.njchunks;
-            pst->jbeg = (item % p.njchunks) * p.jchunk;
-            const int jend = min(pst->jbeg + p.jchunk, p.ntc);
-            pst->nsteps = (jend - pst->jbeg) * nchunks;
+            const int it_row = item / p.njchunks;
+            const int jbeg = (item - it_row * p.njchunks) * p.jchunk;
+            const int jend = min(jbeg + p.jchunk, p.ntc);
+            pst->ti = p.t0 + it_row;
+            pst->J = jbeg; pst->ch = 0;
+            pst->nsteps = (jend - jbeg) * nchunks;
             pst->step = 0;
         }
         const int st = pst->step, ti = pst->ti;
-        const int J = pst->jbeg + st / nchunks;
-        const int ch = st % nchunks;
+        const int J = pst->J, ch = pst->ch;      // (column tile, word chunk) advance without divisions
+        if (ch + 1 == nchunks) { pst->ch = 0; pst->J = J + 1; } else pst->ch = ch + 1;
         const int w0 = ch * KW;
         const int nw = min(KW, p.W - w0);
         m.ti = ti; m.J = J; m.w0 = w0; m.nw = nw;
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
         pst->step = st + 1; pst->count = pr_count + 1;
     };
     if (tid == 0) {
-        pst->count = 0; pst->step = 0; pst->nsteps = 0; pst->ti = 0; pst->jbeg = 0; pst->done = 0;
+        pst->count = 0; pst->step = 0; pst->nsteps = 0; pst->ti = 0; pst->J = 0; pst->ch = 0; pst->done = 0;
         for (int s = 0; s < PK_NS; ++s) { slot_cnt[s] = 0; produce_one(); }
     }
     __syncthreads();

@@ -381,53 +381,93 @@ cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ascending order of the empirical-null p-values WITHOUT a second sort: p is a non-increasing function of |d1|,
+// so it is the merge, by descending magnitude, of the negative run of the sorted d1 (already descending in
+// magnitude) with the reversed non-negative run.  Ties in p get equal adjusted values whatever their order.
+// sorted: d1 ascending, perm1: its permutation.  Outputs sorted_p (ascending) and perm2.
+// ------------------------------------------------------------------------------------------------
+__global__ void p_order_kernel(const double* __restrict__ sorted, const int32_t* __restrict__ perm1, int64_t n,
+                               const double* __restrict__ pval, double* __restrict__ sorted_p,
+                               int32_t* __restrict__ perm2) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    // NaNs sort last (Julia isless): they keep their places and the merge runs over the first nv elements
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] == sorted[mid]) lo = mid + 1; else hi = mid; }
+    const int64_t nv = lo;
+    // m = number of leading negative elements
+    lo = 0; hi = nv;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < 0.0) lo = mid + 1; else hi = mid; }
+    const int64_t m = lo;          // A = sorted[0..m) (magnitudes descending), B = sorted[nv-1 .. m] (descending)
+    const double v = sorted[e];
+    const double mag = fabs(v);
+    int64_t pos;
+    if (v != v) {
+        pos = e;                   // NaNs (sorted last) stay last
+    } else if (e < m) {
+        // A[e]: e elements of A before it + elements of B with magnitude strictly greater
+        int64_t a = m, b = nv;     // B region ascending in value: count of sorted[k] > mag for k in [m, nv)
+        while (a < b) { const int64_t mid = (a + b) >> 1; if (sorted[mid] > mag) b = mid; else a = mid + 1; }
+        pos = e + (nv - a);
+    } else {
+        // B element at reversed index j = n-1-e: j elements of B before it + elements of A with magnitude >= mag
+        int64_t a = 0, b = m;      // A ascending in value (descending magnitude): count of -sorted[k] >= mag
+        while (a < b) { const int64_t mid = (a + b) >> 1; if (-sorted[mid] >= mag) a = mid + 1; else b = mid; }
+        pos = (nv - 1 - e) + a;
+    }
+    const int32_t g = perm1[e];
+    sorted_p[pos] = pval[g];
+    perm2[pos] = g;
+}
+cudaError_t reo_launch_p_order(const double* sorted, const int32_t* perm1, int64_t n, const double* pval,
+                               double* sorted_p, int32_t* perm2, cudaStream_t st) {
+    p_order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted, perm1, n, pval, sorted_p, perm2);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Benjamini-Hochberg, src:413 (MultipleTesting 0.5.1): q_(m) = p_(m) * (n/m), reverse running
 // minimum, min(.,1), un-permute.  One CTA; suffix-min by per-thread chunks + block scan.
 // ------------------------------------------------------------------------------------------------
 #define BH_THREADS 1024
+// One CTA walks the sorted p-values from the top in tiles of 1024 (coalesced), keeping the running minimum:
+// q_(m) = min(q_(m+1), p_(m) * (n/m)); block-wide inclusive suffix-min per tile + carry.
 __global__ void __launch_bounds__(BH_THREADS)
 bh_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64_t n, double* __restrict__ padj) {
-    __shared__ double cmin[72];
-    const int tid = threadIdx.x;
-    const int64_t per = (n + BH_THREADS - 1) / BH_THREADS;
-    const int64_t lo = (int64_t)tid * per, hi = (lo + per < n) ? lo + per : n;
-    double mn = INFINITY;
-    for (int64_t i = hi - 1; i >= lo; --i) {
-        const double q = sp[i] * ((double)n / (double)(i + 1));
-        mn = q < mn ? q : mn;
-    }
-    // exclusive suffix minimum over the per-thread chunk minima (chunks strictly to the right)
-    const int lane = tid & 31, wid = tid >> 5;
-    double inc = mn;  // inclusive suffix min within the warp
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_down_sync(0xffffffffu, inc, o);
-        if (lane + o < 32) inc = t < inc ? t : inc;
-    }
-    double excl = __shfl_down_sync(0xffffffffu, inc, 1);
-    if (lane == 31) excl = INFINITY;
-    if (lane == 0) cmin[wid] = inc;  // warp minimum
+    __shared__ double wmin[32];
+    __shared__ double carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = INFINITY;
     __syncthreads();
-    if (wid == 0) {
-        const double w = cmin[lane];
-        double winc = w;
+    for (int64_t top = n; top > 0; top -= BH_THREADS) {
+        // thread t handles position i = top - 1 - t (descending), so "suffix" = lower thread ids
+        const int64_t i = top - 1 - tid;
+        double q = INFINITY;
+        if (i >= 0) q = sp[i] * ((double)n / (double)(i + 1));
+        double inc = q;  // inclusive min over threads <= tid (positions >= i within the tile)
         for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_down_sync(0xffffffffu, winc, o);
-            if (lane + o < 32) winc = t < winc ? t : winc;
+            const double t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = t < inc ? t : inc;
         }
-        double wex = __shfl_down_sync(0xffffffffu, winc, 1);
-        if (lane == 31) wex = INFINITY;
-        cmin[32 + lane] = wex;  // min over warps strictly to the right
-    }
-    __syncthreads();
-    {
-        const double wr = cmin[32 + wid];
-        excl = wr < excl ? wr : excl;
-    }
-    double run = excl;
-    for (int64_t i = hi - 1; i >= lo; --i) {
-        const double q = sp[i] * ((double)n / (double)(i + 1));
-        run = q < run ? q : run;
-        padj[perm[i]] = run < 1.0 ? run : 1.0;
+        if (lane == 31) wmin[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            double w = wmin[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w = t < w ? t : w;
+            }
+            wmin[lane] = w;  // inclusive min over warps <= lane
+        }
+        __syncthreads();
+        const double carry = carry_s;
+        double run = inc;
+        if (wid > 0) { const double t = wmin[wid - 1]; run = t < run ? t : run; }
+        run = carry < run ? carry : run;
+        if (i >= 0) padj[perm[i]] = run < 1.0 ? run : 1.0;
+        __syncthreads();
+        if (tid == BH_THREADS - 1) carry_s = run;   // min over everything at or above this tile's bottom
+        __syncthreads();
     }
 }
 cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* /*ws*/,

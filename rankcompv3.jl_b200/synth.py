@@ -84,3 +84,29 @@ def random_mask(r, n_ref=3000, seed=MASK_SEED):
     m = np.zeros(r, dtype=bool)
     m[rng.choice(r, min(n_ref, r), replace=False)] = True
     return m
+
+
+def scrna_torch(r=30000, n1=10000, n2=10000, seed=DATA_SEED, device="cuda:0", chunk=1000):
+    """Same model as scrna() but generated on the GPU with torch (seconds instead of minutes at 30k x 20k).
+    Returns (int64 tensor [c, r] row-major == column-major r x c, group list, is_de mask)."""
+    import torch
+    rng = np.random.default_rng(seed)
+    logmu = rng.normal(-1.5, 1.5, r)
+    lfc = _de_structure(rng, r)
+    pz = rng.uniform(0.0, 0.3, r)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    torch.manual_seed(seed)   # _standard_gamma draws from the default generator: make the matrix reproducible
+    out = torch.empty((n1 + n2, r), dtype=torch.int64, device=device)
+    pz_t = torch.as_tensor(pz, device=device, dtype=torch.float32)
+    for (c0, n, lm) in ((0, n1, logmu), (n1, n2, logmu + lfc)):
+        mu = torch.as_tensor(np.exp(lm), device=device, dtype=torch.float32)
+        for s0 in range(0, n, chunk):
+            m = min(chunk, n - s0)
+            # NB(mu, dispersion 0.5) as a gamma-Poisson mixture: gamma(shape 2, scale mu/2)
+            gam = torch._standard_gamma(torch.full((m, r), 2.0, device=device)) * (mu * 0.5)
+            x = torch.poisson(gam, generator=g)
+            x = torch.where(torch.rand((m, r), device=device, generator=g) < pz_t, torch.zeros_like(x), x)
+            out[c0 + s0:c0 + s0 + m] = x.to(torch.int64)
+    group = ["group1"] * n1 + ["group2"] * n2
+    return out, group, lfc != 0

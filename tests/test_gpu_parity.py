@@ -397,3 +397,53 @@ def test_reoa_driver_end_to_end(reo, pkg, tmp_path):
     assert len(out2) <= 600 and list(out2.columns)[1] == "group1_vs_group2"
     with pytest.raises(ValueError, match="ArgumentError"):
         pkg.reoa("nope.txt", "fn_meta.txt", work_dir=str(tmp_path), handle=reo)
+
+
+@pytest.mark.parametrize("n1,n2", [(600, 700), (640, 1000), (1500, 33)])
+def test_many_samples_compare_path(reo, oracle, coracle, n1, n2):
+    """> ~1000 samples: the class lookup tables do not fit and the kernel classifies by comparisons."""
+    data, group = small_case(41, 140, n1, n2, scale=3)
+    levels, gid = oracle.group_levels(group)
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    reo.stage(data, gid, 2)
+    mask = np.arange(140) % 3 != 1
+    tab, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)
+    assert np.array_equal(reo.tables(0, mask, thresholds=thr), tab)
+    rows = np.arange(0, 140, 7)
+    want = oracle.greater_counts(data, gid, 2, rows, rows, seed=7)
+    nre, rest = reo.pair_counts(0, rows, rows)
+    assert np.array_equal(nre, want[0]) and np.array_equal(rest, want[1])
+
+
+def test_full_size_properties_config4(reo, pkg, oracle, coracle):
+    """BASELINE config 4 at full size (30k genes x 10k vs 10k cells, 3000 initial references): properties plus
+    a row block checked against the oracle through a sub-matrix with global gene indices."""
+    import torch
+    dev, group, is_de = pkg.synth.scrna_torch(30000, 10000, 10000)
+    r, c = 30000, 20000
+    levels, gid = oracle.group_levels(group)
+    ref = pkg.synth.reference_mask(is_de, 3000)
+    dm = pkg.DeviceMatrix(dev.data_ptr(), pkg._lib.REO_I64, r, c, r, keepalive=dev)
+    out = reo.identify_degs(dm, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5)
+    tab = out.result[0][:, 2:11].astype(np.int64)
+    fr = out.final_ref[0].astype(bool)
+    assert np.array_equal(tab.sum(axis=1), fr.sum() - fr.astype(int))
+    assert out.stats["compares"] >= 30000 * 3000 * 20000
+    # oracle on a sub-matrix: 24 row genes + 400 of the final reference genes, global indices kept
+    rng = np.random.default_rng(0)
+    rows_g = np.sort(rng.choice(r, 24, replace=False))
+    cols_g = np.sort(rng.choice(np.nonzero(fr)[0], 400, replace=False))
+    genes = np.union1d(rows_g, cols_g)
+    sub = dev[:, torch.as_tensor(genes, device=dev.device)].cpu().numpy().T.astype(np.int64)   # [genes, c]
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    want = coracle.block_tables_idx(sub, genes, gid, 2, thr, np.searchsorted(genes, rows_g), np.searchsorted(genes, cols_g),
+                                    seed=7)
+    mask = np.zeros(r, bool); mask[cols_g] = True
+    got = reo.tables(0, mask, thresholds=thr)   # the matrix staged by identify_degs is still resident
+    assert np.array_equal(got[rows_g], want)
+    res = out.result[0]
+    se_w, p_w = coracle.empirical_null(res[:, 11])
+    assert rel_err(res[:, 0], p_w) <= RTOL and rel_err(res[:, 1], coracle.bh(p_w)) <= RTOL
+    called = out.updown[0] != 0
+    assert called.sum() > 0 and (called & is_de).sum() > 0.5 * called.sum()
+    print("config4:", out.stats)
