@@ -254,7 +254,8 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     const size_t es = dtype_size(dtype);
     if (!data || !group_id || es == 0 || r < 1 || c < 1 || ld < r) return fail(h, REO_ERR_ARG, "reo_stage: bad argument");
     if (gnum < 2) return fail(h, REO_ERR_DIM, "Only 1 level in 'group', at least 2 levels!");
-    if (r > 65535) return fail(h, REO_ERR_UNSUPPORTED, "more than 65535 genes: uint16 dense ranks do not fit");
+    if (r > 131072) return fail(h, REO_ERR_UNSUPPORTED, "more than 131072 genes");
+    const int rank_bytes = r > 65535 ? 4 : 2;   // dense ranks: u16 up to 65535 genes, u32 beyond
     if (c > (int64_t)1 << 24) return fail(h, REO_ERR_UNSUPPORTED, "more than 2^24 samples");
     std::vector<int> lev_n(gnum, 0);
     for (int64_t s = 0; s < c; ++s) {
@@ -300,8 +301,8 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     CK(D.sample_of_slot.ensure(nslots));
     CK(cudaMemcpyAsync(D.slot_of_sample.p, slot_of_sample.data(), c * 4, cudaMemcpyHostToDevice, D.st));
     CK(cudaMemcpyAsync(D.sample_of_slot.p, sample_of_slot.data(), nslots * 4, cudaMemcpyHostToDevice, D.st));
-    CK(D.ranks.ensure((size_t)nslots * rpad));
-    CK(cudaMemsetAsync(D.ranks.p, 0, (size_t)nslots * rpad * sizeof(uint16_t), D.st));
+    CK(D.ranks.ensure((size_t)nslots * rpad * (rank_bytes / 2)));
+    CK(cudaMemsetAsync(D.ranks.p, 0, (size_t)nslots * rpad * rank_bytes, D.st));
     CK(D.flags.ensure(4));
     CK(cudaMemsetAsync(D.flags.p, 0, 4 * sizeof(int), D.st));
     CK(D.fblist.ensure(c));
@@ -321,7 +322,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
             CK(cudaMemcpy2DAsync(D.raw.p + (size_t)c0 * r * es, (size_t)r * es, (const uint8_t*)data + (size_t)c0 * ld * es,
                                  (size_t)ld * es, (size_t)r * es, (size_t)nc, cudaMemcpyHostToDevice, D.st));
         }
-        CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, c0, (int)nc, D.slot_of_sample.p, D.ranks.p, rpad,
+        CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, c0, (int)nc, D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad,
                                    D.flags.p + 2, D.flags.p, D.fblist.p, D.st));
         h->kernel_launches++;
     }
@@ -348,7 +349,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         for (int b0 = 0; b0 < nfb; b0 += batch) {
             const int nb = std::min(batch, nfb - b0);
             CKL(reo_launch_rank_fallback(dev_data, dtype, r, dev_ld, D.fblist.p + b0, nb, D.slot_of_sample.p, D.ranks.p,
-                                        rpad, D.flags.p + 2, D.fb_keys.p, D.fb_rank.p, rp2, D.st));
+                                        rank_bytes, rpad, D.flags.p + 2, D.fb_keys.p, D.fb_rank.p, rp2, D.st));
             h->kernel_launches++;
         }
         CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
@@ -357,11 +358,11 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     const int distinct = std::max(D.h_counts[2], 1);
     int B = 1;
     while ((1 << B) < distinct) ++B;
-    if (B > REO_MAX_BITS) return fail(h, REO_ERR_UNSUPPORTED, "rank needs more than 16 bits");
+    if (B > REO_MAX_BITS) return fail(h, REO_ERR_UNSUPPORTED, "rank needs more than 20 bits");
     S.B = B; S.NP = B + 1;
     CK(D.planes.ensure((size_t)S.NT * S.tile_stride()));
     S.planes = D.planes.p;
-    CKL(reo_launch_bitplanes(D.ranks.p, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
+    CKL(reo_launch_bitplanes(D.ranks.p, rank_bytes, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
                             (uint32_t)(h->seed >> 32), S.planes, D.st));
     h->kernel_launches++;
     }

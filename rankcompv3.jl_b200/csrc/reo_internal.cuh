@@ -14,7 +14,7 @@
 #include "reo.h"
 
 #define REO_TILE 64            // genes per tile
-#define REO_MAX_BITS 16        // rank bits (u16 ranks)
+#define REO_MAX_BITS 20        // rank bits (u16 ranks up to 65535 genes, u32 ranks beyond)
 #define REO_MAX_PLANES (REO_MAX_BITS + 1)
 // float path: one operand word = 64 coin words + 32 samples x 64 genes FP64
 #define REO_FLT_OPWORDS (REO_TILE + 32 * REO_TILE * 2)
@@ -88,14 +88,14 @@ cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word
 
 // staging (reo_stage.cu)
 cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
-                                    const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                    const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                     int* max_distinct, int* flags /*[0]=nonintegral,[1]=n_fallback*/,
                                     int32_t* fallback_list, cudaStream_t st);
 cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* fallback_list,
-                                     int nfb, const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                     int nfb, const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                      int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank,
                                      int64_t rpow2, cudaStream_t st);
-cudaError_t reo_launch_bitplanes(const uint16_t* ranks, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
+cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
                                  int NT, int W, int NP, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes,
                                  cudaStream_t st);
 cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const int32_t* col_gene, int ntc,

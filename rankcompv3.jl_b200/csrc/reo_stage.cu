@@ -71,10 +71,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int* red, int* total) {
     return res;
 }
 
-template <typename T>
+template <typename T, typename RT>
 __global__ void __launch_bounds__(RK_THREADS, 1)
 rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t col0,
-                    const int32_t* __restrict__ slot_of_sample, uint16_t* __restrict__ ranks, int64_t rpad,
+                    const int32_t* __restrict__ slot_of_sample, RT* __restrict__ ranks, int64_t rpad,
                     int* max_distinct, int* flags, int32_t* fallback_list) {
     extern __shared__ uint32_t sm[];
     uint32_t* bm = sm;                   // [BM_WORDS]
@@ -150,7 +150,7 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     __syncthreads();
     // phase 4: dense rank lookup
     const int64_t slot = slot_of_sample[s];
-    uint16_t* __restrict__ out = ranks + slot * rpad;
+    RT* __restrict__ out = ranks + slot * rpad;
     for (int64_t g = tid; g < r; g += RK_THREADS) {
         long long v; to_ll<T>(col[g], v);
         const uint32_t k = (uint32_t)((unsigned long long)v - (unsigned long long)mn);
@@ -158,15 +158,15 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
         uint32_t rk = pre[wq / BM_GROUP];
         for (uint32_t w = (wq / BM_GROUP) * BM_GROUP; w < wq; ++w) rk += __popc(bm[w]);
         rk += __popc(bm[wq] & ((1u << (k & 31)) - 1u));
-        out[g] = (uint16_t)rk;
+        out[g] = (RT)rk;
     }
 }
 
 // ---- fallback: sort-based dense rank in a global-memory scratch (rare: value range > bitmap) ----
-template <typename T>
+template <typename T, typename RT>
 __global__ void __launch_bounds__(RK_THREADS, 1)
 rank_fallback_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* __restrict__ list,
-                     const int32_t* __restrict__ slot_of_sample, uint16_t* __restrict__ ranks, int64_t rpad,
+                     const int32_t* __restrict__ slot_of_sample, RT* __restrict__ ranks, int64_t rpad,
                      int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank, int64_t n) {
     __shared__ int red[40];
     const int tid = threadIdx.x;
@@ -207,28 +207,29 @@ rank_fallback_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const in
     if (tid == 0) atomicMax(max_distinct, total);
     __syncthreads();
     const int64_t slot = slot_of_sample[s];
-    uint16_t* __restrict__ out = ranks + slot * rpad;
+    RT* __restrict__ out = ranks + slot * rpad;
     for (int64_t g = tid; g < r; g += RK_THREADS) {
         long long v; to_ll<T>(col[g], v);
         const unsigned long long key = (unsigned long long)v ^ 0x8000000000000000ull;
         int64_t a = 0, b = r;  // lower_bound
         while (a < b) { const int64_t m = (a + b) >> 1; if (keys[m] < key) a = m + 1; else b = m; }
-        out[g] = (uint16_t)dr[a];
+        out[g] = (RT)dr[a];
     }
 }
 
 static size_t rank_smem_bytes() { return (size_t)(BM_WORDS + BM_PRE + 40) * 4 + 64 * 8 + 16; }
 
 cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
-                                    const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                    const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                     int* max_distinct, int* flags, int32_t* fallback_list, cudaStream_t st) {
     const size_t smem = rank_smem_bytes();
     cudaError_t e;
-#define LAUNCH_RK(T)                                                                                         \
-    e = cudaFuncSetAttribute(rank_columns_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                          \
-    rank_columns_kernel<T><<<ncols, RK_THREADS, smem, st>>>((const T*)data, r, ld, col0, slot_of_sample, ranks, \
-                                                            rpad, max_distinct, flags, fallback_list);
+#define LAUNCH_RK2(T, RT)                                                                                        \
+    e = cudaFuncSetAttribute(rank_columns_kernel<T, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                              \
+    rank_columns_kernel<T, RT><<<ncols, RK_THREADS, smem, st>>>((const T*)data, r, ld, col0, slot_of_sample,     \
+                                                                (RT*)ranks, rpad, max_distinct, flags, fallback_list);
+#define LAUNCH_RK(T) if (rank_bytes == 2) { LAUNCH_RK2(T, uint16_t) } else { LAUNCH_RK2(T, uint32_t) }
     switch (dtype) {
         case REO_I64: LAUNCH_RK(long long); break;
         case REO_F64: LAUNCH_RK(double); break;
@@ -237,16 +238,18 @@ cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int6
         default: return cudaErrorInvalidValue;
     }
 #undef LAUNCH_RK
+#undef LAUNCH_RK2
     return cudaGetLastError();
 }
 
 cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* fallback_list,
-                                     int nfb, const int32_t* slot_of_sample, uint16_t* ranks, int64_t rpad,
+                                     int nfb, const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                      int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank,
                                      int64_t rpow2, cudaStream_t st) {
-#define LAUNCH_FB(T)                                                                                              \
-    rank_fallback_kernel<T><<<nfb, RK_THREADS, 0, st>>>((const T*)data, r, ld, fallback_list, slot_of_sample, ranks, \
-                                                        rpad, max_distinct, scratch_keys, scratch_rank, rpow2);
+#define LAUNCH_FB2(T, RT)                                                                                             \
+    rank_fallback_kernel<T, RT><<<nfb, RK_THREADS, 0, st>>>((const T*)data, r, ld, fallback_list, slot_of_sample,     \
+                                                            (RT*)ranks, rpad, max_distinct, scratch_keys, scratch_rank, rpow2);
+#define LAUNCH_FB(T) if (rank_bytes == 2) { LAUNCH_FB2(T, uint16_t) } else { LAUNCH_FB2(T, uint32_t) }
     switch (dtype) {
         case REO_I64: LAUNCH_FB(long long); break;
         case REO_F64: LAUNCH_FB(double); break;
@@ -255,13 +258,15 @@ cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int
         default: return cudaErrorInvalidValue;
     }
 #undef LAUNCH_FB
+#undef LAUNCH_FB2
     return cudaGetLastError();
 }
 
 // ---- bit-plane transpose ------------------------------------------------------------------------
 // block (64, 4): thread (l, y) builds the NP words of gene t*64+l for sample word w = 4*blockIdx.y+y.
+template <typename RT>
 __global__ void __launch_bounds__(256)
-bitplanes_kernel(const uint16_t* __restrict__ ranks, int64_t rpad, int64_t r,
+bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
                  const int32_t* __restrict__ sample_of_slot, int W, int NP, uint32_t seed_lo, uint32_t seed_hi,
                  uint32_t* __restrict__ planes) {
     const int t = blockIdx.x, l = threadIdx.x;
@@ -290,11 +295,14 @@ bitplanes_kernel(const uint16_t* __restrict__ ranks, int64_t rpad, int64_t r,
         if (p < NP) out[(size_t)p * REO_TILE] = wd[p];
 }
 
-cudaError_t reo_launch_bitplanes(const uint16_t* ranks, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
+cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
                                  int NT, int W, int NP, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes,
                                  cudaStream_t st) {
     dim3 grid(NT, (W + 3) / 4), block(REO_TILE, 4);
-    bitplanes_kernel<<<grid, block, 0, st>>>(ranks, rpad, r, sample_of_slot, W, NP, seed_lo, seed_hi, planes);
+    if (rank_bytes == 2)
+        bitplanes_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)ranks, rpad, r, sample_of_slot, W, NP, seed_lo, seed_hi, planes);
+    else
+        bitplanes_kernel<uint32_t><<<grid, block, 0, st>>>((const uint32_t*)ranks, rpad, r, sample_of_slot, W, NP, seed_lo, seed_hi, planes);
     return cudaGetLastError();
 }
 

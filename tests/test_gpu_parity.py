@@ -447,3 +447,25 @@ def test_full_size_properties_config4(reo, pkg, oracle, coracle):
     called = out.updown[0] != 0
     assert called.sum() > 0 and (called & is_de).sum() > 0.5 * called.sum()
     print("config4:", out.stats)
+
+
+def test_more_than_65535_genes_u32_ranks(reo, oracle, coracle):
+    """> 65 535 genes: dense ranks need more than 16 bits (u32 rank buffer, runtime plane count)."""
+    r = 70000
+    rng = np.random.default_rng(5)
+    data = rng.permutation(r * 13).reshape(r, 13).astype(np.int64)   # tie-free: every column has 70 000 distinct levels
+    data[::50] //= 50                                                # ... except 2 % of the genes, which collide
+    group = ["a"] * 6 + ["b"] * 7
+    levels, gid = oracle.group_levels(group)
+    info = reo.stage(data, gid, 2)
+    assert info["rank_bits"] == 17 and info["gene_tiles"] == -(-r // 64)
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    mask = rng.random(r) < 0.05
+    cols = np.nonzero(mask)[0]
+    got = reo.tables(0, mask, thresholds=thr)
+    for i0 in (0, 33333, 69960):
+        want, _ = coracle.block_tables(data, gid, 2, thr, cols, seed=7, i0=i0, i1=i0 + 40)
+        assert np.array_equal(got[i0:i0 + 40], want)
+    assert np.array_equal(got.sum(axis=1), mask.sum() - mask.astype(int))
+    out = reo.identify_degs(data, gid, 2, mask, 0.01, 1.0, 0.05, 3, 5)
+    assert out.iters[0] >= 1 and out.result.shape == (1, r, 15)
