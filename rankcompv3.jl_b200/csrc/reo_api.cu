@@ -48,6 +48,7 @@ struct NcclApi {
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string err;
     bool load() {
@@ -63,6 +64,7 @@ struct NcclApi {
         REO_NCCL_SYM(CommInitAll, "ncclCommInitAll")
         REO_NCCL_SYM(CommDestroy, "ncclCommDestroy")
         REO_NCCL_SYM(AllGather, "ncclAllGather")
+        REO_NCCL_SYM(AllReduce, "ncclAllReduce")
         REO_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef REO_NCCL_SYM
         return true;
@@ -81,9 +83,9 @@ struct ReoDev {
     ReoStaged S;
     DBuf<uint8_t> raw, raw2, pb, sub;
     DBuf<uint16_t> ranks;
-    DBuf<uint32_t> planes, panel;
+    DBuf<uint32_t> planes, panel, k1_send, k1_gather;
     DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, perm2, counts,
-        fblist, small_i;
+        fblist, small_i, stage_lists;
     DBuf<int8_t> changed_sign, updown;
     DBuf<uint8_t> mask_a, mask_b;
     DBuf<double> result, sorted, sorted_p, se, small_d, std_ws;
@@ -301,46 +303,67 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     CK(D.sample_of_slot.ensure(nslots));
     CK(cudaMemcpyAsync(D.slot_of_sample.p, slot_of_sample.data(), c * 4, cudaMemcpyHostToDevice, D.st));
     CK(cudaMemcpyAsync(D.sample_of_slot.p, sample_of_slot.data(), nslots * 4, cudaMemcpyHostToDevice, D.st));
-    CK(D.ranks.ensure((size_t)nslots * rpad * (rank_bytes / 2)));
-    CK(cudaMemsetAsync(D.ranks.p, 0, (size_t)nslots * rpad * rank_bytes, D.st));
-    CK(D.flags.ensure(4));
-    CK(cudaMemsetAsync(D.flags.p, 0, 4 * sizeof(int), D.st));
-    CK(D.fblist.ensure(c));
 
-    // raw matrix: already on the device, or copied in column chunks that overlap with ranking
+    // K1 sharding (NCCL communicator present): this rank copies, ranks and bit-slices only the sample words
+    // [w_lo, w_hi); the staged blocks are all-gathered over NVLink and re-ordered into planes[t][w].
+    // (small matrices are staged redundantly: two extra collectives cost more than ranking 200 columns)
+    const bool shard = (h->world > 1 && D.comm != nullptr && r * c >= ((int64_t)1 << 24));
+    const int wq = shard ? (W + h->world - 1) / h->world : W;
+    const int w_lo = shard ? std::min(W, h->rank * wq) : 0;
+    const int w_hi = shard ? std::min(W, (h->rank + 1) * wq) : W;
+    std::vector<int32_t> my_samples;   // original sample indices staged by this rank, ascending
+    for (int64_t s = 0; s < c; ++s) {
+        const int w = slot_of_sample[s] / 32;
+        if (w >= w_lo && w < w_hi) my_samples.push_back((int32_t)s);
+    }
+    const int64_t nmy = (int64_t)my_samples.size();
+    const bool on_dev = (flags & REO_DATA_ON_DEVICE) != 0;
+    // list position j -> column of the device matrix (compact copy for host input, the caller's matrix otherwise)
+    std::vector<int32_t> src_col(std::max<int64_t>(nmy, 1)), col_of_sample(c, -1);
+    for (int64_t j = 0; j < nmy; ++j) { src_col[j] = on_dev ? my_samples[j] : (int32_t)j; col_of_sample[my_samples[j]] = src_col[j]; }
+    CK(D.stage_lists.ensure((size_t)2 * std::max<int64_t>(nmy, 1) + c));
+    int32_t* d_src_col = D.stage_lists.p; int32_t* d_sample_id = d_src_col + std::max<int64_t>(nmy, 1);
+    int32_t* d_col_of_sample = d_sample_id + std::max<int64_t>(nmy, 1);
+    if (nmy > 0) {
+        CK(cudaMemcpyAsync(d_src_col, src_col.data(), nmy * 4, cudaMemcpyHostToDevice, D.st));
+        CK(cudaMemcpyAsync(d_sample_id, my_samples.data(), nmy * 4, cudaMemcpyHostToDevice, D.st));
+    }
+    CK(cudaMemcpyAsync(d_col_of_sample, col_of_sample.data(), c * 4, cudaMemcpyHostToDevice, D.st));
+
+    CK(D.ranks.ensure((size_t)nslots * rpad * (rank_bytes / 2)));
+    if (w_hi > w_lo)
+        CK(cudaMemsetAsync((uint8_t*)D.ranks.p + (size_t)w_lo * 32 * rpad * rank_bytes, 0,
+                           (size_t)(w_hi - w_lo) * 32 * rpad * rank_bytes, D.st));
+    CK(D.flags.ensure(8));
+    CK(cudaMemsetAsync(D.flags.p, 0, 8 * sizeof(int), D.st));
+    CK(D.fblist.ensure(std::max<int64_t>(nmy, 1)));
+
+    // raw matrix: already on the device, or copied in runs of consecutive columns that overlap with ranking
     const uint8_t* dev_data = (const uint8_t*)data;
     int64_t dev_ld = ld;
-    if (!(flags & REO_DATA_ON_DEVICE)) {
-        CK(D.raw.ensure((size_t)r * c * es));
+    if (!on_dev) {
+        CK(D.raw.ensure((size_t)r * std::max<int64_t>(nmy, 1) * es));
         dev_data = D.raw.p; dev_ld = r;
     }
     int64_t chunk = std::max<int64_t>(32, (int64_t)(16u << 20) / (int64_t)(r * es));
     chunk = (chunk + 31) / 32 * 32;
-    for (int64_t c0 = 0; c0 < c; c0 += chunk) {
-        const int64_t nc = std::min(chunk, c - c0);
-        if (!(flags & REO_DATA_ON_DEVICE)) {
-            CK(cudaMemcpy2DAsync(D.raw.p + (size_t)c0 * r * es, (size_t)r * es, (const uint8_t*)data + (size_t)c0 * ld * es,
-                                 (size_t)ld * es, (size_t)r * es, (size_t)nc, cudaMemcpyHostToDevice, D.st));
+    for (int64_t j0 = 0; j0 < nmy;) {
+        int64_t n = 1;   // run of consecutive original columns, at most `chunk` long
+        while (j0 + n < nmy && n < chunk && my_samples[j0 + n] == my_samples[j0] + n) ++n;
+        if (!on_dev) {
+            CK(cudaMemcpy2DAsync(D.raw.p + (size_t)j0 * r * es, (size_t)r * es,
+                                 (const uint8_t*)data + (size_t)my_samples[j0] * ld * es, (size_t)ld * es, (size_t)r * es,
+                                 (size_t)n, cudaMemcpyHostToDevice, D.st));
         }
-        CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, c0, (int)nc, D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad,
-                                   D.flags.p + 2, D.flags.p, D.fblist.p, D.st));
+        CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, j0, (int)n, d_src_col, d_sample_id, D.slot_of_sample.p,
+                                    D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p, D.fblist.p, D.st));
         h->kernel_launches++;
+        j0 += n;
     }
     CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
-    if (D.h_counts[0]) {
-        // non-integral values: the 0.1 tie band of is_greater (src:72) is not transitive, so ranks cannot be
-        // used -- stage the raw values as FP64 and let the pair kernel compare them directly
-        if (dtype != REO_F64 && dtype != REO_F32) return fail(h, REO_ERR_ARG, "non-integral values in an integer matrix");
-        S.flt = true; S.B = 0; S.NP = 1;
-        CK(D.planes.ensure((size_t)S.NT * S.tile_stride()));
-        S.planes = D.planes.p;
-        CKL(reo_launch_fstage(dev_data, dtype, r, dev_ld, D.sample_of_slot.p, S.NT, S.W, (uint32_t)h->seed,
-                              (uint32_t)(h->seed >> 32), S.planes, D.st));
-        h->kernel_launches++;
-    } else {
     const int nfb = D.h_counts[1];
-    if (nfb > 0) {
+    if (nfb > 0 && !D.h_counts[0]) {   // columns whose value range exceeds the bitmap: sort-based dense rank
         int64_t rp2 = 1;
         while (rp2 < r) rp2 <<= 1;
         const int batch = std::min(nfb, 2 * D.num_sms);
@@ -348,23 +371,54 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         CK(D.fb_rank.ensure((size_t)batch * rp2));
         for (int b0 = 0; b0 < nfb; b0 += batch) {
             const int nb = std::min(batch, nfb - b0);
-            CKL(reo_launch_rank_fallback(dev_data, dtype, r, dev_ld, D.fblist.p + b0, nb, D.slot_of_sample.p, D.ranks.p,
-                                        rank_bytes, rpad, D.flags.p + 2, D.fb_keys.p, D.fb_rank.p, rp2, D.st));
+            CKL(reo_launch_rank_fallback(dev_data, dtype, r, dev_ld, D.fblist.p + b0, nb, d_src_col, d_sample_id,
+                                         D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.fb_keys.p,
+                                         D.fb_rank.p, rp2, D.st));
             h->kernel_launches++;
         }
-        CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
-        CK(cudaStreamSynchronize(D.st));
     }
-    const int distinct = std::max(D.h_counts[2], 1);
-    int B = 1;
-    while ((1 << B) < distinct) ++B;
-    if (B > REO_MAX_BITS) return fail(h, REO_ERR_UNSUPPORTED, "rank needs more than 20 bits");
-    S.B = B; S.NP = B + 1;
+    if (shard) {   // non-integrality and the largest dense rank are properties of the whole matrix
+        const ncclResult_t nr = g_nccl.AllReduce(D.flags.p, D.flags.p + 4, 4, ncclInt32, ncclMax, D.comm, D.st);
+        if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(nr));
+        CK(cudaMemcpyAsync(D.h_counts, D.flags.p + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
+    } else {
+        CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
+    }
+    CK(cudaStreamSynchronize(D.st));
+    if (D.h_counts[0]) {
+        // non-integral values: the 0.1 tie band of is_greater (src:72) is not transitive, so ranks cannot be
+        // used -- stage the raw values as FP64 and let the pair kernel compare them directly
+        if (dtype != REO_F64 && dtype != REO_F32) return fail(h, REO_ERR_ARG, "non-integral values in an integer matrix");
+        S.flt = true; S.B = 0; S.NP = 1;
+    } else {
+        const int distinct = std::max(D.h_counts[2], 1);
+        int B = 1;
+        while ((1 << B) < distinct) ++B;
+        if (B > REO_MAX_BITS) return fail(h, REO_ERR_UNSUPPORTED, "rank needs more than 20 bits");
+        S.B = B; S.NP = B + 1;
+    }
     CK(D.planes.ensure((size_t)S.NT * S.tile_stride()));
     S.planes = D.planes.p;
-    CKL(reo_launch_bitplanes(D.ranks.p, rank_bytes, rpad, r, D.sample_of_slot.p, S.NT, S.W, S.NP, (uint32_t)h->seed,
-                            (uint32_t)(h->seed >> 32), S.planes, D.st));
+    const size_t wb = S.word_stride();   // words of one (tile, sample word) block
+    uint32_t* stage_out = S.planes;
+    if (shard) {
+        CK(D.k1_send.ensure((size_t)S.NT * wq * wb));
+        CK(D.k1_gather.ensure((size_t)h->world * S.NT * wq * wb));
+        stage_out = D.k1_send.p;
+    }
+    if (S.flt)
+        CKL(reo_launch_fstage(dev_data, dtype, r, dev_ld, D.sample_of_slot.p, d_col_of_sample, S.NT, w_lo, w_hi - w_lo,
+                              shard ? wq : W, (uint32_t)h->seed, (uint32_t)(h->seed >> 32), stage_out, D.st));
+    else
+        CKL(reo_launch_bitplanes(D.ranks.p, rank_bytes, rpad, r, D.sample_of_slot.p, S.NT, w_lo, w_hi - w_lo,
+                                 shard ? wq : W, S.NP, (uint32_t)h->seed, (uint32_t)(h->seed >> 32), stage_out, D.st));
     h->kernel_launches++;
+    if (shard) {
+        const size_t cnt = (size_t)S.NT * wq * wb;
+        const ncclResult_t nr = g_nccl.AllGather(D.k1_send.p, D.k1_gather.p, cnt, ncclUint32, D.comm, D.st);
+        if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclAllGather(planes): ") + g_nccl.GetErrorString(nr));
+        CKL(reo_launch_unshard_planes(D.k1_gather.p, S.planes, S.NT, W, wq, (int)wb, D.st));
+        h->kernel_launches += 2;
     }
     // identity column list for "all genes are references" (cached while r is unchanged)
     if (D.iota_r != r) {
@@ -597,6 +651,7 @@ int reo_destroy(reo_handle_t h) {
         cudaSetDevice(D.dev);
         if (D.st) cudaStreamSynchronize(D.st);
         if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
+        D.k1_send.release(); D.k1_gather.release(); D.stage_lists.release();
         D.raw.release(); D.raw2.release(); D.pb.release(); D.sub.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
         D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
         D.changed_gene.release(); D.table.release(); D.perm.release(); D.perm2.release(); D.counts.release(); D.fblist.release();

@@ -86,23 +86,29 @@ cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word
                                          int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB,
                                          cudaStream_t st);
 
-// staging (reo_stage.cu)
+// staging (reo_stage.cu).  Columns are addressed through lists so that a rank can stage only its share:
+// list position j -> data column src_col[j], original sample sample_id[j].
 cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
+                                    const int32_t* src_col, const int32_t* sample_id,
                                     const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                     int* max_distinct, int* flags /*[0]=nonintegral,[1]=n_fallback*/,
                                     int32_t* fallback_list, cudaStream_t st);
 cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* fallback_list,
-                                     int nfb, const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
+                                     int nfb, const int32_t* src_col, const int32_t* sample_id,
+                                     const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                      int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank,
                                      int64_t rpow2, cudaStream_t st);
 cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
-                                 int NT, int W, int NP, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes,
-                                 cudaStream_t st);
+                                 int NT, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo, uint32_t seed_hi,
+                                 uint32_t* planes, cudaStream_t st);
+cudaError_t reo_launch_unshard_planes(const uint32_t* gathered, uint32_t* planes, int NT, int W, int wq, int wb,
+                                      cudaStream_t st);
 cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const int32_t* col_gene, int ntc,
                                     uint32_t* panel, cudaStream_t st);
 
-cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* sample_of_slot, int NT,
-                              int W, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes, cudaStream_t st);
+cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* sample_of_slot,
+                              const int32_t* col_of_sample, int NT, int w_lo, int w_n, int w_stride, uint32_t seed_lo,
+                              uint32_t seed_hi, uint32_t* planes, cudaStream_t st);
 cudaError_t reo_launch_gather_panel_flt(const uint32_t* planes, int W, const int32_t* col_gene, int ntc, uint32_t* panel,
                                         cudaStream_t st);
 

@@ -74,6 +74,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* red, int* total) {
 template <typename T, typename RT>
 __global__ void __launch_bounds__(RK_THREADS, 1)
 rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t col0,
+                    const int32_t* __restrict__ src_col, const int32_t* __restrict__ sample_id,
                     const int32_t* __restrict__ slot_of_sample, RT* __restrict__ ranks, int64_t rpad,
                     int* max_distinct, int* flags, int32_t* fallback_list) {
     extern __shared__ uint32_t sm[];
@@ -83,8 +84,9 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     long long* redl = (long long*)(red + 40);  // [64]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t s = col0 + blockIdx.x;
-    const T* __restrict__ col = data + ld * s;
+    const int64_t j = col0 + blockIdx.x;          // position in this rank's column list
+    const int64_t s = sample_id[j];               // original sample index (slot lookup, fallback list)
+    const T* __restrict__ col = data + ld * (int64_t)src_col[j];
 
     // phase 1: min / max / integrality
     long long mn = LLONG_MAX, mx = LLONG_MIN;
@@ -112,7 +114,7 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     }
     const unsigned long long range = (unsigned long long)mx - (unsigned long long)mn;
     if (range >= (unsigned long long)BM_WORDS * 32ull) {
-        if (tid == 0) { int k = atomicAdd(&flags[1], 1); fallback_list[k] = (int32_t)s; }
+        if (tid == 0) { int k = atomicAdd(&flags[1], 1); fallback_list[k] = (int32_t)j; }
         return;
     }
     // phase 2: presence bitmap of (v - min)
@@ -166,12 +168,14 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
 template <typename T, typename RT>
 __global__ void __launch_bounds__(RK_THREADS, 1)
 rank_fallback_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* __restrict__ list,
+                     const int32_t* __restrict__ src_col, const int32_t* __restrict__ sample_id,
                      const int32_t* __restrict__ slot_of_sample, RT* __restrict__ ranks, int64_t rpad,
                      int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank, int64_t n) {
     __shared__ int red[40];
     const int tid = threadIdx.x;
-    const int64_t s = list[blockIdx.x];
-    const T* __restrict__ col = data + ld * s;
+    const int64_t j = list[blockIdx.x];
+    const int64_t s = sample_id[j];
+    const T* __restrict__ col = data + ld * (int64_t)src_col[j];
     unsigned long long* keys = scratch_keys + (int64_t)blockIdx.x * n;
     uint32_t* dr = scratch_rank + (int64_t)blockIdx.x * n;
     for (int64_t g = tid; g < n; g += RK_THREADS) {
@@ -220,6 +224,7 @@ rank_fallback_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const in
 static size_t rank_smem_bytes() { return (size_t)(BM_WORDS + BM_PRE + 40) * 4 + 64 * 8 + 16; }
 
 cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
+                                    const int32_t* src_col, const int32_t* sample_id,
                                     const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                     int* max_distinct, int* flags, int32_t* fallback_list, cudaStream_t st) {
     const size_t smem = rank_smem_bytes();
@@ -227,7 +232,7 @@ cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int6
 #define LAUNCH_RK2(T, RT)                                                                                        \
     e = cudaFuncSetAttribute(rank_columns_kernel<T, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                              \
-    rank_columns_kernel<T, RT><<<ncols, RK_THREADS, smem, st>>>((const T*)data, r, ld, col0, slot_of_sample,     \
+    rank_columns_kernel<T, RT><<<ncols, RK_THREADS, smem, st>>>((const T*)data, r, ld, col0, src_col, sample_id, slot_of_sample, \
                                                                 (RT*)ranks, rpad, max_distinct, flags, fallback_list);
 #define LAUNCH_RK(T) if (rank_bytes == 2) { LAUNCH_RK2(T, uint16_t) } else { LAUNCH_RK2(T, uint32_t) }
     switch (dtype) {
@@ -243,11 +248,12 @@ cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int6
 }
 
 cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* fallback_list,
-                                     int nfb, const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
+                                     int nfb, const int32_t* src_col, const int32_t* sample_id,
+                                     const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
                                      int* max_distinct, unsigned long long* scratch_keys, uint32_t* scratch_rank,
                                      int64_t rpow2, cudaStream_t st) {
 #define LAUNCH_FB2(T, RT)                                                                                             \
-    rank_fallback_kernel<T, RT><<<nfb, RK_THREADS, 0, st>>>((const T*)data, r, ld, fallback_list, slot_of_sample,     \
+    rank_fallback_kernel<T, RT><<<nfb, RK_THREADS, 0, st>>>((const T*)data, r, ld, fallback_list, src_col, sample_id, slot_of_sample, \
                                                             (RT*)ranks, rpad, max_distinct, scratch_keys, scratch_rank, rpow2);
 #define LAUNCH_FB(T) if (rank_bytes == 2) { LAUNCH_FB2(T, uint16_t) } else { LAUNCH_FB2(T, uint32_t) }
     switch (dtype) {
@@ -267,11 +273,13 @@ cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int
 template <typename RT>
 __global__ void __launch_bounds__(256)
 bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
-                 const int32_t* __restrict__ sample_of_slot, int W, int NP, uint32_t seed_lo, uint32_t seed_hi,
-                 uint32_t* __restrict__ planes) {
+                 const int32_t* __restrict__ sample_of_slot, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo,
+                 uint32_t seed_hi, uint32_t* __restrict__ planes) {
+    // words [w_lo, w_lo + w_n) of the staged order are written at local index (w - w_lo) with w_stride words per tile
     const int t = blockIdx.x, l = threadIdx.x;
-    const int w = blockIdx.y * 4 + threadIdx.y;
-    if (w >= W) return;
+    const int wl = blockIdx.y * 4 + threadIdx.y;
+    if (wl >= w_n) return;
+    const int w = w_lo + wl;
     const int64_t g = (int64_t)t * REO_TILE + l;
     uint32_t wd[REO_MAX_PLANES];
 #pragma unroll
@@ -289,20 +297,21 @@ bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
             }
         }
     }
-    uint32_t* out = planes + ((size_t)t * W + w) * NP * REO_TILE + l;
+    uint32_t* out = planes + ((size_t)t * w_stride + wl) * NP * REO_TILE + l;
 #pragma unroll
     for (int p = 0; p < REO_MAX_PLANES; ++p)
         if (p < NP) out[(size_t)p * REO_TILE] = wd[p];
 }
 
 cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
-                                 int NT, int W, int NP, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes,
-                                 cudaStream_t st) {
-    dim3 grid(NT, (W + 3) / 4), block(REO_TILE, 4);
+                                 int NT, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo, uint32_t seed_hi,
+                                 uint32_t* planes, cudaStream_t st) {
+    if (w_n <= 0) return cudaSuccess;
+    dim3 grid(NT, (w_n + 3) / 4), block(REO_TILE, 4);
     if (rank_bytes == 2)
-        bitplanes_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)ranks, rpad, r, sample_of_slot, W, NP, seed_lo, seed_hi, planes);
+        bitplanes_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, seed_lo, seed_hi, planes);
     else
-        bitplanes_kernel<uint32_t><<<grid, block, 0, st>>>((const uint32_t*)ranks, rpad, r, sample_of_slot, W, NP, seed_lo, seed_hi, planes);
+        bitplanes_kernel<uint32_t><<<grid, block, 0, st>>>((const uint32_t*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, seed_lo, seed_hi, planes);
     return cudaGetLastError();
 }
 
@@ -336,16 +345,17 @@ cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const
 // planes[t][w] = [64 coin words][32 samples][64 genes] FP64 raw values (pad slots / pad genes = 0.0)
 template <typename T>
 __global__ void __launch_bounds__(256)
-fstage_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* __restrict__ sample_of_slot, int W,
-              uint32_t seed_lo, uint32_t seed_hi, uint32_t* __restrict__ planes) {
-    const int t = blockIdx.x, w = blockIdx.y, l = threadIdx.x, y = threadIdx.y;
+fstage_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* __restrict__ sample_of_slot,
+              const int32_t* __restrict__ col_of_sample, int w_lo, int w_stride, uint32_t seed_lo, uint32_t seed_hi,
+              uint32_t* __restrict__ planes) {
+    const int t = blockIdx.x, wl = blockIdx.y, w = w_lo + wl, l = threadIdx.x, y = threadIdx.y;
     const int64_t g = (int64_t)t * REO_TILE + l;
-    uint32_t* base = planes + ((size_t)t * W + w) * REO_FLT_OPWORDS;
+    uint32_t* base = planes + ((size_t)t * w_stride + wl) * REO_FLT_OPWORDS;
     double* vals = reinterpret_cast<double*>(base + REO_TILE);
     for (int sidx = y; sidx < 32; sidx += 4) {
         const int so = sample_of_slot[(int64_t)w * 32 + sidx];
         double v = 0.0;
-        if (so >= 0 && g < r) v = (double)data[(int64_t)so * ld + g];
+        if (so >= 0 && g < r) v = (double)data[(int64_t)col_of_sample[so] * ld + g];
         vals[sidx * REO_TILE + l] = v;
     }
     if (y == 0) {
@@ -360,12 +370,14 @@ fstage_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* 
     }
 }
 
-cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* sample_of_slot, int NT,
-                              int W, uint32_t seed_lo, uint32_t seed_hi, uint32_t* planes, cudaStream_t st) {
-    dim3 grid(NT, W), block(REO_TILE, 4);
+cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* sample_of_slot,
+                              const int32_t* col_of_sample, int NT, int w_lo, int w_n, int w_stride, uint32_t seed_lo,
+                              uint32_t seed_hi, uint32_t* planes, cudaStream_t st) {
+    if (w_n <= 0) return cudaSuccess;
+    dim3 grid(NT, w_n), block(REO_TILE, 4);
     switch (dtype) {
-        case REO_F64: fstage_kernel<double><<<grid, block, 0, st>>>((const double*)data, r, ld, sample_of_slot, W, seed_lo, seed_hi, planes); break;
-        case REO_F32: fstage_kernel<float><<<grid, block, 0, st>>>((const float*)data, r, ld, sample_of_slot, W, seed_lo, seed_hi, planes); break;
+        case REO_F64: fstage_kernel<double><<<grid, block, 0, st>>>((const double*)data, r, ld, sample_of_slot, col_of_sample, w_lo, w_stride, seed_lo, seed_hi, planes); break;
+        case REO_F32: fstage_kernel<float><<<grid, block, 0, st>>>((const float*)data, r, ld, sample_of_slot, col_of_sample, w_lo, w_stride, seed_lo, seed_hi, planes); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -390,5 +402,23 @@ cudaError_t reo_launch_gather_panel_flt(const uint32_t* planes, int W, const int
     if (ntc <= 0) return cudaSuccess;
     dim3 grid(ntc, W);
     gather_panel_flt_kernel<<<grid, 256, 0, st>>>(planes, W, col_gene, panel);
+    return cudaGetLastError();
+}
+
+
+// ---- K1 sharded over ranks: gathered[q][t][wl][wb] (rank q staged words q*wq .. ) -> planes[t][w][wb] ----
+__global__ void __launch_bounds__(256)
+unshard_planes_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ planes, int NT, int W, int wq, int wb4) {
+    // one CTA per (tile, word); wb4 = operand words / 4 (16-byte units)
+    const int t = blockIdx.x, w = blockIdx.y;
+    const int q = w / wq, wl = w - q * wq;
+    const uint4* src = gathered + (((size_t)q * NT + t) * wq + wl) * wb4;
+    uint4* dst = planes + ((size_t)t * W + w) * wb4;
+    for (int i = threadIdx.x; i < wb4; i += blockDim.x) dst[i] = src[i];
+}
+cudaError_t reo_launch_unshard_planes(const uint32_t* gathered, uint32_t* planes, int NT, int W, int wq, int wb,
+                                      cudaStream_t st) {
+    dim3 grid(NT, W);
+    unshard_planes_kernel<<<grid, 256, 0, st>>>((const uint4*)gathered, (uint4*)planes, NT, W, wq, wb / 4);
     return cudaGetLastError();
 }
