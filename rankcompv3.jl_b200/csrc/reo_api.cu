@@ -660,6 +660,7 @@ int reo_destroy(reo_handle_t h) {
         D.counter.release(); D.flags.release(); D.fb_keys.release(); D.fb_rank.release(); D.small_ll.release();
         if (D.sortws.keys) cudaFree(D.sortws.keys);
         if (D.sortws.idx) cudaFree(D.sortws.idx);
+        if (D.sortws.pos) cudaFree(D.sortws.pos);
         if (D.h_counts) cudaFreeHost(D.h_counts);
         if (D.h_out) cudaFreeHost(D.h_out);
         D.std_ws.release();

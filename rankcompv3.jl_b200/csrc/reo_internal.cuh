@@ -127,6 +127,7 @@ cudaError_t reo_launch_mccullagh_kxk(const int64_t* tables, int64_t n, int k, do
 struct ReoSortWs {  // workspace for reo_sort
     unsigned long long* keys = nullptr;  // chunk-sorted keys
     uint32_t* idx = nullptr;
+    int32_t* pos = nullptr;
     int64_t cap = 0;
 };
 cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,

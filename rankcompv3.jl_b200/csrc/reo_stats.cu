@@ -139,7 +139,7 @@ cudaError_t reo_launch_mccullagh_kxk(const int64_t* tables, int64_t n, int k, do
 // stable ascending sort of doubles: chunk bitonic sort in shared memory + cross-chunk ranking.
 // Total order = (Julia isless key, original index): -0.0 < 0.0, NaN last.
 // ------------------------------------------------------------------------------------------------
-#define SORT_CHUNK 2048
+#define SORT_CHUNK 1024
 #define SORT_THREADS 1024
 
 __device__ __forceinline__ unsigned long long f64_key(double x) {
@@ -151,74 +151,65 @@ __device__ __forceinline__ bool kv_less(unsigned long long ka, uint32_t ia, unsi
     return ka < kb || (ka == kb && ia < ib);
 }
 
+// One element per thread; bitonic network with warp shuffles for partner distances < 32 and one
+// double-buffered shared-memory exchange (single barrier) for the larger ones.
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_chunks_kernel(const double* __restrict__ x, int64_t n, unsigned long long* __restrict__ keys,
-                   uint32_t* __restrict__ idx) {
-    __shared__ unsigned long long sk[SORT_CHUNK];
-    __shared__ uint32_t si[SORT_CHUNK];
-    const int64_t base = (int64_t)blockIdx.x * SORT_CHUNK;
-    for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) {
-        const int64_t g = base + i;
-        sk[i] = g < n ? f64_key(x[g]) : ~0ull;
-        si[i] = g < n ? (uint32_t)g : 0xffffffffu;
-    }
-    __syncthreads();
-    for (int k = 2; k <= SORT_CHUNK; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool asc = (i & k) == 0;
-                    const unsigned long long a = sk[i], b = sk[l];
-                    const uint32_t ia = si[i], ib = si[l];
-                    const bool gt = kv_less(b, ib, a, ia);
-                    if (gt == asc) { sk[i] = b; sk[l] = a; si[i] = ib; si[l] = ia; }
-                }
+                   uint32_t* __restrict__ idx, int32_t* __restrict__ pos) {
+    __shared__ unsigned long long sk[2][SORT_CHUNK];
+    __shared__ uint32_t si[2][SORT_CHUNK];
+    const int t = threadIdx.x;
+    const int64_t g = (int64_t)blockIdx.x * SORT_CHUNK + t;
+    unsigned long long k = g < n ? f64_key(x[g]) : ~0ull;
+    uint32_t i = g < n ? (uint32_t)g : 0xffffffffu;
+    int buf = 0;
+    for (int kk = 2; kk <= SORT_CHUNK; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            unsigned long long ok; uint32_t oi;
+            if (j >= 32) {
+                sk[buf][t] = k; si[buf][t] = i;
+                __syncthreads();
+                ok = sk[buf][t ^ j]; oi = si[buf][t ^ j];
+                buf ^= 1;
+            } else {
+                ok = __shfl_xor_sync(0xffffffffu, k, j); oi = __shfl_xor_sync(0xffffffffu, i, j);
             }
-            __syncthreads();
+            const bool asc = (t & kk) == 0, lower = (t & j) == 0;
+            const bool other_less = kv_less(ok, oi, k, i);
+            // the lower index of an ascending pair keeps the minimum, the upper the maximum (reversed if descending)
+            if ((lower == asc) == other_less) { k = ok; i = oi; }
         }
-    for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) { keys[base + i] = sk[i]; idx[base + i] = si[i]; }
+    }
+    keys[g] = k; idx[g] = i; pos[g] = t;
 }
 
-// One CTA per chunk A: every other chunk B is staged in shared memory in turn and each element of A
-// counts the elements of B below it (binary search in shared memory); final position = sum of counts.
+// grid (A, B): every element of chunk A counts the elements of chunk B below it (binary search in shared memory)
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_rank_kernel(const double* __restrict__ x, int64_t n, int nchunks,
-                 const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx,
-                 double* __restrict__ sorted, int32_t* __restrict__ perm) {
+sort_cross_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx, int32_t* __restrict__ pos) {
     __shared__ unsigned long long sk[SORT_CHUNK];
     __shared__ uint32_t si[SORT_CHUNK];
-    const int mych = blockIdx.x;
-    const int64_t base = (int64_t)mych * SORT_CHUNK;
-    constexpr int PER = SORT_CHUNK / SORT_THREADS;
-    unsigned long long ke[PER];
-    uint32_t ie[PER];
-    int pos[PER];
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int e = threadIdx.x + q * SORT_THREADS;
-        ke[q] = keys[base + e]; ie[q] = idx[base + e]; pos[q] = e;
-    }
-    for (int ch = 0; ch < nchunks; ++ch) {
-        if (ch == mych) continue;
-        __syncthreads();
-        for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) {
-            sk[i] = keys[(int64_t)ch * SORT_CHUNK + i]; si[i] = idx[(int64_t)ch * SORT_CHUNK + i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            int a = 0, b = SORT_CHUNK;  // number of elements of chunk ch that are < (ke, ie)
-            while (a < b) { const int m = (a + b) >> 1; if (kv_less(sk[m], si[m], ke[q], ie[q])) a = m + 1; else b = m; }
-            pos[q] += a;
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        if (ie[q] == 0xffffffffu) continue;
-        sorted[pos[q]] = x[ie[q]];
-        if (perm) perm[pos[q]] = (int32_t)ie[q];
-    }
+    const int A = blockIdx.x, B = blockIdx.y, t = threadIdx.x;
+    if (A == B) return;
+    sk[t] = keys[(int64_t)B * SORT_CHUNK + t]; si[t] = idx[(int64_t)B * SORT_CHUNK + t];
+    const unsigned long long ke = keys[(int64_t)A * SORT_CHUNK + t];
+    const uint32_t ie = idx[(int64_t)A * SORT_CHUNK + t];
+    __syncthreads();
+    if (ie == 0xffffffffu) return;
+    int a = 0, b = SORT_CHUNK;
+    while (a < b) { const int m = (a + b) >> 1; if (kv_less(sk[m], si[m], ke, ie)) a = m + 1; else b = m; }
+    if (a) atomicAdd(&pos[(int64_t)A * SORT_CHUNK + t], a);
+}
+
+__global__ void sort_scatter_kernel(const double* __restrict__ x, int64_t total, const uint32_t* __restrict__ idx,
+                                    const int32_t* __restrict__ pos, double* __restrict__ sorted,
+                                    int32_t* __restrict__ perm) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const uint32_t ie = idx[e];
+    if (ie == 0xffffffffu) return;
+    const int32_t p = pos[e];
+    sorted[p] = x[ie];
+    if (perm) perm[p] = (int32_t)ie;
 }
 
 cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,
@@ -229,15 +220,22 @@ cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int3
     if (ws.cap < need) {
         if (ws.keys) cudaFree(ws.keys);
         if (ws.idx) cudaFree(ws.idx);
-        ws.keys = nullptr; ws.idx = nullptr; ws.cap = 0;
+        if (ws.pos) cudaFree(ws.pos);
+        ws.keys = nullptr; ws.idx = nullptr; ws.pos = nullptr; ws.cap = 0;
         cudaError_t e = cudaMalloc(&ws.keys, need * sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
         e = cudaMalloc(&ws.idx, need * sizeof(uint32_t));
         if (e != cudaSuccess) return e;
+        e = cudaMalloc(&ws.pos, need * sizeof(int32_t));
+        if (e != cudaSuccess) return e;
         ws.cap = need;
     }
-    sort_chunks_kernel<<<nchunks, SORT_THREADS, 0, st>>>(x, n, ws.keys, ws.idx);
-    sort_rank_kernel<<<nchunks, SORT_THREADS, 0, st>>>(x, n, nchunks, ws.keys, ws.idx, sorted, perm);
+    sort_chunks_kernel<<<nchunks, SORT_THREADS, 0, st>>>(x, n, ws.keys, ws.idx, ws.pos);
+    if (nchunks > 1) {
+        dim3 grid(nchunks, nchunks);
+        sort_cross_kernel<<<grid, SORT_THREADS, 0, st>>>(ws.keys, ws.idx, ws.pos);
+    }
+    sort_scatter_kernel<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(x, need, ws.idx, ws.pos, sorted, perm);
     return cudaGetLastError();
 }
 
@@ -247,7 +245,6 @@ cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int3
 // combined in the exact tree order by one thread.
 // ------------------------------------------------------------------------------------------------
 #define STD_MAX_LEAVES 256
-#define STD_CHUNK 256
 
 struct StdFrame { int64_t lo, hi; int state; double v1; };
 
@@ -290,14 +287,15 @@ __device__ int std_leaf_bounds(int64_t lo0, int64_t hi0, int want, int64_t* lo_o
     return nl;
 }
 
-// PASS 0: leaf sums of x -> mean.  PASS 1: leaf sums of (x-mean)^2 -> se.  One warp per leaf: lanes
-// stage 256 values at a time in shared memory (coalesced), lane 0 adds them strictly left to right;
-// the last CTA to finish combines the leaves in tree order.  ws: [0..255] leaf sums, [256] mean.
+// PASS 0: leaf sums of x -> mean.  PASS 1: leaf sums of (x-mean)^2 -> se.  One warp per leaf: lane l holds the
+// values lo + 32k + l in registers (32 coalesced loads in flight), then every lane forms the SAME strictly
+// left-to-right sum by pulling value after value out of its owner with a shuffle; the last CTA to finish combines
+// the leaves in tree order.  ws: [0..255] leaf sums, [256] mean.
 template <int PASS>
 __global__ void __launch_bounds__(32)
 std_leaf_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ ws,
                 unsigned int* __restrict__ done, double* __restrict__ se_out) {
-    __shared__ double buf[STD_CHUNK];
+    __shared__ double buf[STD_MAX_LEAVES];
     __shared__ StdFrame frames[64];
     __shared__ int64_t b_lo, b_hi;
     __shared__ int last;
@@ -305,24 +303,25 @@ std_leaf_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, dou
     if (lane == 0) std_leaf_bounds(lo0, hi0, blockIdx.x, &b_lo, &b_hi, frames);
     __syncwarp();
     const int64_t lo = b_lo, hi = b_hi;
+    const int cnt = (int)(hi - lo + 1);                    // <= 1024
     const double mean = PASS ? ws[STD_MAX_LEAVES] : 0.0;
+    double reg[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int i = k * 32 + lane;
+        double xv = 0.0;
+        if (i < cnt) { xv = sorted[lo + i]; if (PASS) xv = (xv - mean) * (xv - mean); }
+        reg[k] = xv;
+    }
     double v = 0.0;
-    for (int64_t c0 = lo; c0 <= hi; c0 += STD_CHUNK) {
-        const int cnt = (int)((hi - c0 + 1 < STD_CHUNK) ? hi - c0 + 1 : STD_CHUNK);
-        __syncwarp();
-        for (int i = lane; i < cnt; i += 32) {
-            const double xv = sorted[c0 + i];
-            buf[i] = PASS ? (xv - mean) * (xv - mean) : xv;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            int i = 0;
-            if (c0 == lo) {
-                if (cnt == 1) { v = buf[0]; i = 1; }
-                else { v = buf[0] + buf[1]; i = 2; }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k * 32 < cnt) {                                 // warp-uniform
+            const int m = (cnt - k * 32 < 32) ? cnt - k * 32 : 32;
+            for (int l = 0; l < m; ++l) {
+                const double xv = __shfl_sync(0xffffffffu, reg[k], l);
+                v = (k == 0 && l == 0) ? xv : v + xv;       // f(a1) + f(a2), then + f(a_i) left to right
             }
-#pragma unroll 8
-            for (; i < cnt; ++i) v = v + buf[i];
         }
     }
     if (lane == 0) {
@@ -334,9 +333,8 @@ std_leaf_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, dou
     if (last && lane == 0) {
         __threadfence();
         const volatile double* vw = ws;
-        double* leaf = buf;  // reuse shared memory for the leaf sums (<= 256)
-        for (int l = 0; l < (int)gridDim.x; ++l) leaf[l] = vw[l];
-        const double tot = std_combine(lo0, hi0, leaf, frames);
+        for (int l = 0; l < (int)gridDim.x; ++l) buf[l] = vw[l];
+        const double tot = std_combine(lo0, hi0, buf, frames);
         const int64_t m = hi0 - lo0 + 1;
         if (PASS == 0) ws[STD_MAX_LEAVES] = tot / (double)m;
         else *se_out = sqrt(tot / (double)(m - 1));
