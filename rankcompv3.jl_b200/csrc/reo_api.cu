@@ -471,7 +471,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     p.ntc = ntc;
     const int ntr = p.t1 - p.t0;
     if (ntr <= 0) return REO_OK;
-    const int want_items = 8 * 3 * D.num_sms;
+    const int want_items = 16 * 3 * D.num_sms;   // ~16 work items per resident CTA: small tail
     int njc = std::max(1, std::min(ntc, (want_items + ntr - 1) / ntr));
     p.jchunk = (ntc + njc - 1) / njc;
     p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;

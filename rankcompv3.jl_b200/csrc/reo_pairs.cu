@@ -435,15 +435,25 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
         }
         if (m.flags & PKF_LAST_J) {
             // group B finished: look up the bin, add to the shared table
+            if (all_valid) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int gi = gi0 + a;
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t off = binB(acc[a][b], a * 4 + b);
-                    if (all_valid || (gj[b] >= 0 && gi != gj[b] && gi < p.r)) {
-                        const uint32_t addr = tab_row_s + off + (uint32_t)(a * 4);
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t addr = tab_row_s + binB(acc[a][b], a * 4 + b) + (uint32_t)(a * 4);
                         asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(sgn[b]) : "memory");
+                    }
+            } else {   // pad columns, rows beyond r, self pairs: only on the matrix edges and the diagonal
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int gi = gi0 + a;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t off = binB(acc[a][b], a * 4 + b);
+                        if (gj[b] >= 0 && gi != gj[b] && gi < p.r) {
+                            const uint32_t addr = tab_row_s + off + (uint32_t)(a * 4);
+                            asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(sgn[b]) : "memory");
+                        }
                     }
                 }
             }
