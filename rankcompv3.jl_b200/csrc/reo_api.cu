@@ -103,6 +103,11 @@ struct ReoDev {
     int n_pev = 0;
     int64_t iota_r = -1;
     ncclComm_t comm = nullptr;    // set by reo_comm_init_rank / multi-device reo_create
+    // the per-evaluation statistics sequence (K3..K6) as a CUDA graph, one per mask ping-pong direction
+    cudaGraphExec_t eval_exec[2] = {nullptr, nullptr};
+    std::vector<const void*> eval_key;
+    int64_t eval_r = -1;
+    double eval_pd = 0.0, eval_qd = 0.0;
 };
 
 struct reo_handle_s {
@@ -523,6 +528,57 @@ int allgather_tables(reo_handle_t h, ReoDev& D) {
     return REO_OK;
 }
 
+// One evaluation of src:402-417 on the current tables: McCullagh per gene, sort + trimmed std, empirical-null p,
+// BH, new mask, symmetric difference, and the three counters the host decides on (read back into pinned memory).
+int enqueue_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double padj_deg, uint8_t* mask_cur,
+                 uint8_t* mask_new) {
+    CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));                                   // src:402-406
+    CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, D.perm.p, D.sortws, D.st));     // src:409
+    CKL(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, D.std_ws.p, D.st));                               // src:411
+    CKL(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));               // src:412
+    // src:413: the ascending order of p follows from the sorted d1 (p decreases with |d1|): no second sort
+    CKL(reo_launch_p_order(D.sorted.p, D.perm.p, r, D.result.p, D.sorted_p.p, D.perm2.p, D.st));
+    CKL(reo_launch_bh(D.sorted_p.p, D.perm2.p, r, D.result.p + r, nullptr, D.st));
+    CKL(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));            // src:417
+    CKL(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
+    CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+    return REO_OK;
+}
+
+void drop_eval_graphs(ReoDev& D) {
+    for (auto& e : D.eval_exec) { if (e) cudaGraphExecDestroy(e); e = nullptr; }
+}
+
+// Launch the evaluation sequence as one CUDA graph (11 small kernels: the launch gaps otherwise dominate).
+int run_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double padj_deg, uint8_t* mask_cur,
+             uint8_t* mask_new) {
+    h->kernel_launches += 11;  // mccullagh, sort x3, std x2, pvals, p_order, bh, inds, diff
+    static const bool no_graph = getenv("REO_NO_GRAPH") != nullptr;
+    if (debug_sync() || no_graph) return enqueue_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new);
+    CK(reo_sort_reserve(D.sortws, r));
+    const std::vector<const void*> key = {D.table.p, D.result.p, D.sorted.p, D.perm.p, D.sorted_p.p, D.perm2.p, D.se.p,
+                                          D.counts.p, D.changed_gene.p, D.changed_sign.p, D.sortws.keys, D.std_ws.p,
+                                          D.mask_a.p, D.mask_b.p, D.h_counts};
+    if (key != D.eval_key || r != D.eval_r || pval_deg != D.eval_pd || padj_deg != D.eval_qd) {
+        drop_eval_graphs(D);
+        D.eval_key = key; D.eval_r = r; D.eval_pd = pval_deg; D.eval_qd = padj_deg;
+    }
+    const int which = (mask_cur == D.mask_a.p) ? 0 : 1;
+    if (!D.eval_exec[which]) {
+        CK(cudaStreamBeginCapture(D.st, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(D.st, &g);
+        if (rc != REO_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail_cuda(h, e, "cudaStreamEndCapture");
+        const cudaError_t e2 = cudaGraphInstantiate(&D.eval_exec[which], g, 0);
+        cudaGraphDestroy(g);
+        if (e2 != cudaSuccess) { D.eval_exec[which] = nullptr; return fail_cuda(h, e2, "cudaGraphInstantiate"); }
+    }
+    CK(cudaGraphLaunch(D.eval_exec[which], D.st));
+    return REO_OK;
+}
+
 // run f(rank handle, rank) on every device of a multi-device handle, one host thread per device
 template <typename F>
 int run_multi(reo_handle_t parent, F f) {
@@ -651,6 +707,7 @@ int reo_destroy(reo_handle_t h) {
         cudaSetDevice(D.dev);
         if (D.st) cudaStreamSynchronize(D.st);
         if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
+        drop_eval_graphs(D);
         D.k1_send.release(); D.k1_gather.release(); D.stage_lists.release();
         D.raw.release(); D.raw2.release(); D.pb.release(); D.sub.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
         D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
@@ -1028,20 +1085,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
                 have_tables = true;
             }
             if ((rc = allgather_tables(h, D))) return rc;
-            // src:402-406
-            CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
-            // src:409-412
-            CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, D.perm.p, D.sortws, D.st));
-            CKL(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, D.std_ws.p, D.st));
-            CKL(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));
-            // src:413: the ascending order of p follows from the sorted d1 (p decreases with |d1|): no second sort
-            CKL(reo_launch_p_order(D.sorted.p, D.perm.p, r, D.result.p, D.sorted_p.p, D.perm2.p, D.st));
-            CKL(reo_launch_bh(D.sorted_p.p, D.perm2.p, r, D.result.p + r, nullptr, D.st));
-            // src:417
-            CKL(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));
-            CKL(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
-            h->kernel_launches += 10;  // mccullagh, sort x2, std x2, pvals, p_order, bh, inds, diff
-            CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+            if ((rc = run_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new))) return rc;
             CK(cudaStreamSynchronize(D.st));
             const int n_ref = D.h_counts[0], n_inds = D.h_counts[1], n_chg = D.h_counts[2];
             if (n_eval < REO_MAX_ITER_LOG) { st_local.n_deg[n_eval] = (int32_t)r - n_inds; st_local.n_ref[n_eval] = n_ref; }

@@ -130,6 +130,7 @@ struct ReoSortWs {  // workspace for reo_sort
     int32_t* pos = nullptr;
     int64_t cap = 0;
 };
+cudaError_t reo_sort_reserve(ReoSortWs& ws, int64_t n);
 cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,
                                 cudaStream_t st);
 cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* leaf_ws, cudaStream_t st);

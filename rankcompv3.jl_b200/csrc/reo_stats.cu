@@ -212,6 +212,26 @@ __global__ void sort_scatter_kernel(const double* __restrict__ x, int64_t total,
     if (perm) perm[p] = (int32_t)ie;
 }
 
+// make sure the workspace holds n elements (allocation must not happen while a stream is being captured)
+cudaError_t reo_sort_reserve(ReoSortWs& ws, int64_t n) {
+    const int nchunks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
+    const int64_t need = (int64_t)nchunks * SORT_CHUNK;
+    if (ws.cap < need) {
+        if (ws.keys) cudaFree(ws.keys);
+        if (ws.idx) cudaFree(ws.idx);
+        if (ws.pos) cudaFree(ws.pos);
+        ws.keys = nullptr; ws.idx = nullptr; ws.pos = nullptr; ws.cap = 0;
+        cudaError_t e = cudaMalloc(&ws.keys, need * sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&ws.idx, need * sizeof(uint32_t));
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&ws.pos, need * sizeof(int32_t));
+        if (e != cudaSuccess) return e;
+        ws.cap = need;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,
                                 cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
