@@ -538,7 +538,7 @@ int enqueue_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double p
     CKL(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));               // src:412
     // src:413: the ascending order of p follows from the sorted d1 (p decreases with |d1|): no second sort
     CKL(reo_launch_p_order(D.sorted.p, D.perm.p, r, D.result.p, D.sorted_p.p, D.perm2.p, D.st));
-    CKL(reo_launch_bh(D.sorted_p.p, D.perm2.p, r, D.result.p + r, nullptr, D.st));
+    CKL(reo_launch_bh(D.sorted_p.p, D.perm2.p, r, D.result.p + r, D.sorted.p /* free after p_order: scratch */, D.st));
     CKL(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));            // src:417
     CKL(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
     CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
@@ -914,7 +914,7 @@ int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj) {
     CK(cudaMemcpyAsync(d_x, p, n * 8, cudaMemcpyHostToDevice, D.st));
     if (n > 1) {
         CKL(reo_launch_sort_f64(d_x, n, d_s, D.perm.p, D.sortws, D.st));
-        CKL(reo_launch_bh(d_s, D.perm.p, n, d_q, nullptr, D.st));
+        CKL(reo_launch_bh(d_s, D.perm.p, n, d_q, d_x /* input already sorted into d_s: scratch */, D.st));
     } else {
         d_q = d_x;
     }
@@ -1085,7 +1085,15 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
                 have_tables = true;
             }
             if ((rc = allgather_tables(h, D))) return rc;
+            static const bool timing = getenv("REO_TIMING") != nullptr;
+            if (timing) CK(cudaEventRecord(D.ev[3], D.st));
             if ((rc = run_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new))) return rc;
+            if (timing) {
+                CK(cudaEventRecord(D.ev[4], D.st));
+                CK(cudaEventSynchronize(D.ev[4]));
+                float ms = 0; cudaEventElapsedTime(&ms, D.ev[3], D.ev[4]);
+                fprintf(stderr, "[reo timing]   evaluation %d: statistics sequence %.3f ms\n", n_eval, ms);
+            }
             CK(cudaStreamSynchronize(D.st));
             const int n_ref = D.h_counts[0], n_inds = D.h_counts[1], n_chg = D.h_counts[2];
             if (n_eval < REO_MAX_ITER_LOG) { st_local.n_deg[n_eval] = (int32_t)r - n_inds; st_local.n_ref[n_eval] = n_ref; }

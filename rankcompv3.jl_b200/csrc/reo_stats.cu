@@ -336,11 +336,17 @@ std_leaf_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, dou
     double v = 0.0;
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-        if (k * 32 < cnt) {                                 // warp-uniform
-            const int m = (cnt - k * 32 < 32) ? cnt - k * 32 : 32;
-            for (int l = 0; l < m; ++l) {
+        if (k * 32 + 32 <= cnt) {                           // warp-uniform: a full row of 32
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
                 const double xv = __shfl_sync(0xffffffffu, reg[k], l);
                 v = (k == 0 && l == 0) ? xv : v + xv;       // f(a1) + f(a2), then + f(a_i) left to right
+            }
+        } else if (k * 32 < cnt) {
+            const int m = cnt - k * 32;
+            for (int l = 0; l < m; ++l) {
+                const double xv = __shfl_sync(0xffffffffu, reg[k], l);
+                v = (k == 0 && l == 0) ? xv : v + xv;
             }
         }
     }
@@ -407,16 +413,22 @@ cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se,
 __global__ void p_order_kernel(const double* __restrict__ sorted, const int32_t* __restrict__ perm1, int64_t n,
                                const double* __restrict__ pval, double* __restrict__ sorted_p,
                                int32_t* __restrict__ perm2) {
+    __shared__ int64_t nv_s, m_s;
+    if (threadIdx.x == 0) {
+        // NaNs sort last (Julia isless): they keep their places and the merge runs over the first nv elements
+        int64_t lo = 0, hi = n;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] == sorted[mid]) lo = mid + 1; else hi = mid; }
+        nv_s = lo;
+        // m = number of leading negative elements
+        hi = lo; lo = 0;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < 0.0) lo = mid + 1; else hi = mid; }
+        m_s = lo;
+    }
+    __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    // NaNs sort last (Julia isless): they keep their places and the merge runs over the first nv elements
-    int64_t lo = 0, hi = n;
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] == sorted[mid]) lo = mid + 1; else hi = mid; }
-    const int64_t nv = lo;
-    // m = number of leading negative elements
-    lo = 0; hi = nv;
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < 0.0) lo = mid + 1; else hi = mid; }
-    const int64_t m = lo;          // A = sorted[0..m) (magnitudes descending), B = sorted[nv-1 .. m] (descending)
+    const int64_t nv = nv_s;
+    const int64_t m = m_s;         // A = sorted[0..m) (magnitudes descending), B = sorted[nv-1 .. m] (descending)
     const double v = sorted[e];
     const double mag = fabs(v);
     int64_t pos;
@@ -448,49 +460,48 @@ cudaError_t reo_launch_p_order(const double* sorted, const int32_t* perm1, int64
 // minimum, min(.,1), un-permute.  One CTA; suffix-min by per-thread chunks + block scan.
 // ------------------------------------------------------------------------------------------------
 #define BH_THREADS 1024
-// One CTA walks the sorted p-values from the top in tiles of 1024 (coalesced), keeping the running minimum:
-// q_(m) = min(q_(m+1), p_(m) * (n/m)); block-wide inclusive suffix-min per tile + carry.
+// q_(m) = min(q_(m+1), p_(m) * (n/m)): reverse running minimum.  Each warp owns a contiguous segment (coalesced
+// rows of 32), scans it from the top with shuffles (partial result parked in `scratch`), then adds the minimum of
+// the warps to its right.  One barrier.
 __global__ void __launch_bounds__(BH_THREADS)
-bh_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64_t n, double* __restrict__ padj) {
-    __shared__ double wmin[32];
-    __shared__ double carry_s;
+bh_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64_t n, double* __restrict__ padj,
+          double* __restrict__ scratch) {
+    __shared__ double wtot[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = INFINITY;
+    const int64_t seg = ((n + 31) / 32 + 31) / 32 * 32;          // elements per warp, multiple of 32
+    const int64_t lo = (int64_t)wid * seg;
+    const int64_t hi = (lo + seg < n) ? lo + seg : n;             // [lo, hi)
+    const int rows = (hi > lo) ? (int)((hi - lo + 31) / 32) : 0;
+    double carry = INFINITY;
+    for (int rr = rows - 1; rr >= 0; --rr) {
+        const int64_t i = lo + (int64_t)rr * 32 + lane;
+        double v = INFINITY;
+        if (i < hi) v = sp[i] * ((double)n / (double)(i + 1));
+        for (int o = 1; o < 32; o <<= 1) {                        // inclusive suffix minimum over lanes >= lane
+            const double t = __shfl_down_sync(0xffffffffu, v, o);
+            if (lane + o < 32) v = t < v ? t : v;
+        }
+        v = carry < v ? carry : v;
+        if (i < hi) scratch[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 0);
+    }
+    if (lane == 0) wtot[wid] = carry;   // minimum of this warp's whole segment (INFINITY if empty)
     __syncthreads();
-    for (int64_t top = n; top > 0; top -= BH_THREADS) {
-        // thread t handles position i = top - 1 - t (descending), so "suffix" = lower thread ids
-        const int64_t i = top - 1 - tid;
-        double q = INFINITY;
-        if (i >= 0) q = sp[i] * ((double)n / (double)(i + 1));
-        double inc = q;  // inclusive min over threads <= tid (positions >= i within the tile)
-        for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc = t < inc ? t : inc;
+    double right = INFINITY;            // minimum over the warps to the right
+    for (int w = wid + 1; w < 32; ++w) { const double t = wtot[w]; right = t < right ? t : right; }
+    for (int rr = 0; rr < rows; ++rr) {
+        const int64_t i = lo + (int64_t)rr * 32 + lane;
+        if (i < hi) {
+            double v = scratch[i];      // written by this very thread
+            v = right < v ? right : v;
+            padj[perm[i]] = v < 1.0 ? v : 1.0;
         }
-        if (lane == 31) wmin[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            double w = wmin[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w = t < w ? t : w;
-            }
-            wmin[lane] = w;  // inclusive min over warps <= lane
-        }
-        __syncthreads();
-        const double carry = carry_s;
-        double run = inc;
-        if (wid > 0) { const double t = wmin[wid - 1]; run = t < run ? t : run; }
-        run = carry < run ? carry : run;
-        if (i >= 0) padj[perm[i]] = run < 1.0 ? run : 1.0;
-        __syncthreads();
-        if (tid == BH_THREADS - 1) carry_s = run;   // min over everything at or above this tile's bottom
-        __syncthreads();
     }
 }
-cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* /*ws*/,
+cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* ws,
                           cudaStream_t st) {
-    bh_kernel<<<1, BH_THREADS, 0, st>>>(sorted_p, perm, n, padj);
+    if (!ws) return cudaErrorInvalidValue;   // n doubles of scratch
+    bh_kernel<<<1, BH_THREADS, 0, st>>>(sorted_p, perm, n, padj, ws);
     return cudaGetLastError();
 }
 
