@@ -319,8 +319,12 @@ def main():
         W = st_dev[-1]["sample_words"]
         # LOP3 lane-ops actually issued: (B+1) per 32 sample slots, padded words included
         lop3 = k2_cmp / c * (W * 32) * (B + 1) / 32.0
+        # DRAM traffic of the dominant launch from the ncu --set full capture in profiles/r01_pair_kernel_ncu.md
+        # (dram__bytes_read.sum + dram__bytes_write.sum, delta build of the default workload: 13.6 MB ~= the staged
+        # row planes + column panel read once; everything else is served by L2, hit rate 98 %)
+        traffic = 13.6e6 if args.workload == "c2_bulk_20kx200" else None
         roof = {"bound": "alu", "achieved": ach / 1e9, "peak": p_cmp / 1e9, "unit": "Gcmp/s", "frac": ach / p_cmp,
-                "traffic": None,
+                "traffic": traffic, "traffic_note": "bytes per launch of the largest pair-kernel launch (ncu, profiles/)",
                 "note": "compare-ALU roofline of BASELINE.md (SMs x 128 lanes x measured SM clock, 'of measured' clock; "
                         "fallback 1965 MHz if nvidia-smi gave no sample); bit-sliced LOP3 evaluates 32 samples per lane-op",
                 "kernel": "reo_pair_kernel", "launches": k2_launches, "ms_per_launch": k2_ms / max(k2_launches, 1),
