@@ -469,3 +469,65 @@ def test_more_than_65535_genes_u32_ranks(reo, oracle, coracle):
     assert np.array_equal(got.sum(axis=1), mask.sum() - mask.astype(int))
     out = reo.identify_degs(data, gid, 2, mask, 0.01, 1.0, 0.05, 3, 5)
     assert out.iters[0] >= 1 and out.result.shape == (1, r, 15)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+def test_edge_cases_match_oracle(reo, oracle, coracle):
+    rng = np.random.default_rng(9)
+    gid = np.array([0] * 6 + [1] * 7, dtype=np.int32)
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    cases = {
+        "all ties (constant matrix)": np.full((60, 13), 5, dtype=np.int64),
+        "two values only": rng.integers(0, 2, size=(60, 13)).astype(np.int64),
+        "negative counts": rng.integers(-50, 50, size=(60, 13)).astype(np.int64),
+        "tie-free": np.stack([rng.permutation(60) for _ in range(13)], axis=1).astype(np.int64),
+    }
+    for name, data in cases.items():
+        for ref in (np.ones(60, bool), np.zeros(60, bool), np.arange(60) == 7, np.arange(60) % 2 == 0):
+            want = coracle.identify_degs(data, gid, 2, thr, 1.0, 0.05, ref, 8, 1, seed=7)
+            out = reo.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 8, 1)
+            check_full(out, want)
+    # one sample in a group, interleaved columns, explicit leading dimension (ld > r through a Fortran-order slice)
+    big = np.asfortranarray(rng.integers(0, 30, size=(90, 21)).astype(np.int64))
+    view = big[:77, :]                      # column-major view with ld = 90 -> the wrapper copies to ld = r
+    gid2 = np.array([1] + [0] * 20, dtype=np.int32)[rng.permutation(21)]
+    gid2 = np.where(gid2 == gid2[0], 0, 1).astype(np.int32)   # level ids in order of first appearance
+    thr2 = coracle.thresholds_for(gid2, 2, 0.01)
+    ref = np.arange(77) % 3 == 0
+    want = coracle.identify_degs(view, gid2, 2, thr2, 1.0, 0.05, ref, 8, 1, seed=7)
+    check_full(reo.identify_degs(view, gid2, 2, ref, 0.01, 1.0, 0.05, 8, 1), want)
+
+
+def test_error_behaviour_matches_reference(reo, pkg):
+    data = np.random.default_rng(0).integers(0, 9, size=(10, 8)).astype(np.int64)
+    gid = np.array([0, 0, 0, 0, 1, 1, 1, 1], dtype=np.int32)
+    with pytest.raises(IndexError):                       # r <= 10: BoundsError at src:411
+        reo.identify_degs(data, gid, 2, np.ones(10, bool))
+    data = np.random.default_rng(0).integers(0, 9, size=(30, 8)).astype(np.int64)
+    with pytest.raises(ValueError, match="DimensionMismatch"):   # src:355
+        reo.identify_degs(data, gid[:7], 2, np.ones(30, bool))
+    with pytest.raises(ValueError, match="DimensionMismatch"):   # src:356: one level only
+        reo.identify_degs(data, np.zeros(8, np.int32), 1, np.ones(30, bool))
+    with pytest.raises(ValueError, match="DimensionMismatch"):   # a declared level without samples
+        reo.identify_degs(data, np.zeros(8, np.int32), 2, np.ones(30, bool))
+    out = reo.identify_degs(data, gid, 2, np.ones(30, bool), n_iter=0)   # while i_iter < 0: never entered -> zeros
+    assert out.iters == [0] and not out.result.any() and not out.updown.any()
+    with pytest.raises(ValueError, match="ArgumentError"):
+        pkg.Reo(9999)                                      # bad device index: loud failure, no fallback
+
+
+def test_c_driver_example(tmp_path):
+    """examples/reo_driver.c: the ABI from plain C (no Python in the process)."""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "reo_driver")
+    lib_dir = os.path.join(ROOT, "rankcompv3.jl_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "reo_driver.c"), "-o", exe, "-L" + lib_dir, "-lreo_cuda",
+                           "-Wl,-rpath," + lib_dir, "-Wl,--allow-shlib-undefined"])
+    out = subprocess.run([exe, "3000", "20", "24"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "Convergence threshold is reached" in out.stdout or "iteration" in out.stdout
+    last = [l for l in out.stdout.splitlines() if l.startswith("genes")][0].split()
+    called_up, planted_hit = int(last[7]), int(last[11])
+    assert called_up > 100 and planted_hit > 100, out.stdout
