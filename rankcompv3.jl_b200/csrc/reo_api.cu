@@ -350,8 +350,14 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         CK(D.raw.ensure((size_t)r * std::max<int64_t>(nmy, 1) * es));
         dev_data = D.raw.p; dev_ld = r;
     }
-    int64_t chunk = std::max<int64_t>(32, (int64_t)(16u << 20) / (int64_t)(r * es));
-    chunk = (chunk + 31) / 32 * 32;
+    // columns per rank launch: one CTA per column and one CTA per SM, so whole waves of SMs; host input is copied
+    // in chunks of ~64 MB so that the copy of chunk n+1 overlaps the ranking of chunk n
+    int64_t chunk = nmy;
+    if (!on_dev) {
+        chunk = std::max<int64_t>(1, (int64_t)(64u << 20) / (int64_t)(r * es));
+        chunk = std::max<int64_t>(D.num_sms, chunk / D.num_sms * D.num_sms);
+    }
+    chunk = std::max<int64_t>(chunk, 1);
     for (int64_t j0 = 0; j0 < nmy;) {
         int64_t n = 1;   // run of consecutive original columns, at most `chunk` long
         while (j0 + n < nmy && n < chunk && my_samples[j0 + n] == my_samples[j0] + n) ++n;

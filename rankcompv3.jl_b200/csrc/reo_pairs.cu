@@ -147,8 +147,22 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+#ifndef PK_WARP_SHAPE
+#define PK_WARP_SHAPE 0
+#endif
+#if PK_WARP_SHAPE == 0      // warp = 8 x 4 threads: 32 rows x 16 columns
     const int ty = (warp >> 2) * 8 + (lane >> 2);   // 0..15 : rows ty*4 .. ty*4+3
     const int tx = (warp & 3) * 4 + (lane & 3);     // 0..15 : cols tx*4 .. tx*4+3
+#elif PK_WARP_SHAPE == 1    // warp = 4 x 8 threads: 16 rows x 32 columns
+    const int ty = (warp >> 1) * 4 + (lane >> 3);
+    const int tx = (warp & 1) * 8 + (lane & 7);
+#elif PK_WARP_SHAPE == 2    // warp = 2 x 16 threads: 8 rows x 64 columns
+    const int ty = warp * 2 + (lane >> 4);
+    const int tx = lane & 15;
+#else                       // warp = 16 x 2 threads: 64 rows x 8 columns
+    const int ty = (warp >> 3) * 16 + (lane >> 1);
+    const int tx = (warp & 7) * 2 + (lane & 1);
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < PK_NS; ++s) mbar_init(&full[s], 1);
