@@ -331,6 +331,17 @@ def main():
                 "kernel_share_of_step": k2_ms / ms_dev if ms_dev > 0 else None,
                 "lop3_pipe_frac": (lop3 / (k2_ms * 1e-3)) / (n_sms * 64 * sm_mhz * 1e6) if k2_ms > 0 else None,
                 "rank_bits": B, "sample_words": W, "sm_mhz_used": sm_mhz}
+        # K1 (rank + bit-plane staging) against the measured HBM copy bandwidth: SURVEY 8d algorithmic bytes =
+        # read r*c*8 (Int64 input) + write r*c*2 (dense ranks).  Not the dominant kernel (3-4 % of a job).
+        k1_ms = sum(s["ms_stage"] for s in st_dev) / len(st_dev)
+        k1_bytes = float(r) * c * 8 + float(r) * c * 2
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        roof_k1 = {"bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None, "peak": hbm_peak,
+                   "unit": "GB/s", "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9) / hbm_peak if k1_ms > 0 else None,
+                   "traffic": None, "ms": k1_ms, "kernel": "rank_columns_kernel + bitplanes_kernel",
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                   "note": "occupancy/latency-bound, not bandwidth-bound: one 1024-thread CTA per sample column and one "
+                           "CTA per SM (185 KB presence bitmap); small inputs cannot fill the GPU"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -347,7 +358,7 @@ def main():
             "stage_ms": {"staging": st_dev[-1]["ms_stage"], "pairs": st_dev[-1]["ms_pairs"],
                          "stats": st_dev[-1]["ms_stats"], "total_device": st_dev[-1]["ms_total"],
                          "call_wall": st_dev[-1]["ms_wall"]},
-            "clocks": clocks, "roofline": roof,
+            "clocks": clocks, "roofline": roof, "roofline_staging": roof_k1,
         }
         if probe is not None:
             line["scaling_probe"] = probe
