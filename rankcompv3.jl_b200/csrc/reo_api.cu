@@ -79,6 +79,8 @@ struct ReoDev {
     int dev = 0;
     int num_sms = 148;
     cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr;      // host->device copies of the matrix, overlapped with ranking on `st`
+    std::vector<cudaEvent_t> copy_ev;    // one per in-flight chunk
     cudaEvent_t ev[8] = {};
     ReoStaged S;
     DBuf<uint8_t> raw, raw2, pb, sub;
@@ -351,20 +353,34 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         dev_data = D.raw.p; dev_ld = r;
     }
     // columns per rank launch: one CTA per column and one CTA per SM, so whole waves of SMs; host input is copied
-    // in chunks of ~64 MB so that the copy of chunk n+1 overlaps the ranking of chunk n
+    // in chunks of >= 16 MB so that the copy of chunk n+1 overlaps the ranking of chunk n
     int64_t chunk = nmy;
     if (!on_dev) {
-        chunk = std::max<int64_t>(1, (int64_t)(64u << 20) / (int64_t)(r * es));
+        chunk = std::max<int64_t>(1, (int64_t)(16u << 20) / (int64_t)(r * es));
         chunk = std::max<int64_t>(D.num_sms, chunk / D.num_sms * D.num_sms);
     }
     chunk = std::max<int64_t>(chunk, 1);
+    if (!on_dev) {   // the copy stream must not overtake work still queued on `st` that reads/frees `raw`
+        CK(cudaEventRecord(D.ev[5], D.st));
+        CK(cudaStreamWaitEvent(D.st_copy, D.ev[5], 0));
+    }
+    size_t n_chunk = 0;
     for (int64_t j0 = 0; j0 < nmy;) {
         int64_t n = 1;   // run of consecutive original columns, at most `chunk` long
         while (j0 + n < nmy && n < chunk && my_samples[j0 + n] == my_samples[j0] + n) ++n;
         if (!on_dev) {
+            // copy on the copy stream, rank on the compute stream as soon as this chunk has landed
             CK(cudaMemcpy2DAsync(D.raw.p + (size_t)j0 * r * es, (size_t)r * es,
                                  (const uint8_t*)data + (size_t)my_samples[j0] * ld * es, (size_t)ld * es, (size_t)r * es,
-                                 (size_t)n, cudaMemcpyHostToDevice, D.st));
+                                 (size_t)n, cudaMemcpyHostToDevice, D.st_copy));
+            if (n_chunk >= D.copy_ev.size()) {
+                cudaEvent_t ev;
+                CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                D.copy_ev.push_back(ev);
+            }
+            CK(cudaEventRecord(D.copy_ev[n_chunk], D.st_copy));
+            CK(cudaStreamWaitEvent(D.st, D.copy_ev[n_chunk], 0));
+            ++n_chunk;
         }
         CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, j0, (int)n, d_src_col, d_sample_id, D.slot_of_sample.p,
                                     D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p, D.fblist.p, D.st));
@@ -630,6 +646,10 @@ static int create_single(reo_handle_t* out, int dev, uint64_t seed) {
         return fail(nullptr, REO_ERR_CUDA, std::string("reo_create: ") + cudaGetErrorString(e));
     }
     cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, D.dev);
+    if ((e = cudaStreamCreateWithFlags(&D.st_copy, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h; cudaGetLastError();
+        return fail(nullptr, REO_ERR_CUDA, std::string("reo_create: ") + cudaGetErrorString(e));
+    }
     for (auto& ev : D.ev) cudaEventCreate(&ev);
     if (cudaMallocHost((void**)&D.h_counts, 16 * sizeof(int32_t)) != cudaSuccess) {
         delete h; cudaGetLastError();
@@ -729,6 +749,8 @@ int reo_destroy(reo_handle_t h) {
         D.std_ws.release();
         for (auto& ev : D.ev) if (ev) cudaEventDestroy(ev);
         for (auto& ev : D.pev) cudaEventDestroy(ev);
+        for (auto& ev : D.copy_ev) cudaEventDestroy(ev);
+        if (D.st_copy) cudaStreamDestroy(D.st_copy);
         if (D.st) cudaStreamDestroy(D.st);
     }
     delete h;
