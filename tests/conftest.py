@@ -17,6 +17,10 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def pkg():
+    """The package, with libreo_cuda.so built if this checkout has not been built yet (nvcc cross-compiles)."""
+    so = os.path.join(ge.PKG_DIR, "libreo_cuda.so")
+    if not os.path.exists(so):
+        ge.build()
     return ge.load_package()
 
 
