@@ -166,3 +166,27 @@ def test_golden_bundled_block(coracle):
     cols2 = np.nonzero(g["final_ref"])[0]
     tab2, _ = coracle.block_tables(g["data"], g["gid"], 2, g["thr"], cols2, seed=int(g["seed"]), i0=1000, i1=1064)
     assert np.array_equal(tab2, g["tables"][1000:1064])
+
+
+def test_tie_coins_are_fair_and_mirrored(oracle):
+    """The deterministic tie rule is equal in distribution to the reference's rand(Bool) (src:72-73) for a
+    gene's comparisons: over seeds, the number of ties a gene wins out of T is Binomial(T, 1/2), and the
+    partner always gets the complement (mirror property, src:385-386)."""
+    T = 64
+    data = np.zeros((3, T), dtype=np.int64)          # genes 0, 1, 2 tie in every sample
+    gid = np.zeros(T, dtype=np.int32)
+    wins01, wins02, wins10 = [], [], []
+    for seed in range(1500):
+        cnt = oracle.greater_counts(data, gid, 1, [0, 1], [0, 1, 2], seed=seed)[0]
+        wins01.append(cnt[0, 1]); wins02.append(cnt[0, 2]); wins10.append(cnt[1, 0])
+    w01, w02, w10 = np.array(wins01), np.array(wins02), np.array(wins10)
+    assert np.all(w01 + w10 == T)                                   # mirror, exactly
+    for w in (w01, w02):
+        assert abs(w.mean() - T / 2) < 0.5 and abs(w.var() - T / 4) < 2.5   # Binomial(64, 1/2): mean 32, var 16
+    assert abs(np.corrcoef(w01, w02)[0, 1]) < 0.1                   # a gene's coins against different partners
+    # histogram against the exact binomial pmf (chi-square on pooled bins, dof ~ 12, 1e-4 critical value ~ 40)
+    from scipy.stats import binom
+    edges = [0, 25, 27, 29, 30, 31, 32, 33, 34, 35, 36, 38, 40, 65]
+    obs = np.histogram(w01, bins=edges)[0]
+    exp = np.diff(binom.cdf(np.array(edges) - 1, T, 0.5)) * len(w01)
+    assert ((obs - exp) ** 2 / exp).sum() < 40
