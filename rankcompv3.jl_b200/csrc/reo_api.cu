@@ -87,7 +87,7 @@ struct ReoDev {
     DBuf<uint16_t> ranks;
     DBuf<uint32_t> planes, panel, k1_send, k1_gather;
     DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, perm2, counts,
-        fblist, small_i, stage_lists;
+        fblist, widelist, small_i, stage_lists;
     DBuf<int8_t> changed_sign, updown;
     DBuf<uint8_t> mask_a, mask_b;
     DBuf<double> result, sorted, sorted_p, se, small_d, std_ws;
@@ -344,6 +344,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     CK(D.flags.ensure(8));
     CK(cudaMemsetAsync(D.flags.p, 0, 8 * sizeof(int), D.st));
     CK(D.fblist.ensure(std::max<int64_t>(nmy, 1)));
+    CK(D.widelist.ensure(std::max<int64_t>(nmy, 1)));
 
     // raw matrix: already on the device, or copied in runs of consecutive columns that overlap with ranking
     const uint8_t* dev_data = (const uint8_t*)data;
@@ -365,6 +366,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         CK(cudaStreamWaitEvent(D.st_copy, D.ev[5], 0));
     }
     size_t n_chunk = 0;
+    const bool small_first = c >= 1024;   // heuristic only: either order of tiers gives the same ranks
     for (int64_t j0 = 0; j0 < nmy;) {
         int64_t n = 1;   // run of consecutive original columns, at most `chunk` long
         while (j0 + n < nmy && n < chunk && my_samples[j0 + n] == my_samples[j0] + n) ++n;
@@ -382,13 +384,30 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
             CK(cudaStreamWaitEvent(D.st, D.copy_ev[n_chunk], 0));
             ++n_chunk;
         }
-        CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, j0, (int)n, d_src_col, d_sample_id, D.slot_of_sample.p,
-                                    D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p, D.fblist.p, D.st));
+        // tier 0: small presence bitmap (value range < 65536), 8 CTAs per SM; wider columns are listed for tier 1.
+        // Bulk inputs (few samples, counts up to ~1e6) would all overflow it, so they start at tier 1 directly.
+        if (small_first)
+            CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, j0, (int)n, nullptr, 0, d_src_col, d_sample_id,
+                                        D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p,
+                                        D.flags.p + 3, D.widelist.p, D.st));
+        else
+            CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, j0, (int)n, nullptr, 1, d_src_col, d_sample_id,
+                                        D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p,
+                                        D.flags.p + 1, D.fblist.p, D.st));
         h->kernel_launches++;
         j0 += n;
     }
     CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
+    if (D.h_counts[3] > 0 && !D.h_counts[0]) {
+        // tier 1: 1.3 M-value bitmap, one CTA per SM; still wider columns are listed for the sort-based fallback
+        CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, 0, D.h_counts[3], D.widelist.p, 1, d_src_col, d_sample_id,
+                                    D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p,
+                                    D.flags.p + 1, D.fblist.p, D.st));
+        h->kernel_launches++;
+        CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
+    }
     const int nfb = D.h_counts[1];
     if (nfb > 0 && !D.h_counts[0]) {   // columns whose value range exceeds the bitmap: sort-based dense rank
         int64_t rp2 = 1;
@@ -734,7 +753,7 @@ int reo_destroy(reo_handle_t h) {
         if (D.st) cudaStreamSynchronize(D.st);
         if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
         drop_eval_graphs(D);
-        D.k1_send.release(); D.k1_gather.release(); D.stage_lists.release();
+        D.k1_send.release(); D.k1_gather.release(); D.stage_lists.release(); D.widelist.release();
         D.raw.release(); D.raw2.release(); D.pb.release(); D.sub.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
         D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
         D.changed_gene.release(); D.table.release(); D.perm.release(); D.perm2.release(); D.counts.release(); D.fblist.release();

@@ -15,11 +15,11 @@
 
 #include "reo_internal.cuh"
 
-#define RK_THREADS 1024
-#define BM_WORDS 40960                  // bitmap words in shared memory (1,310,720 distinct values)
+#define RK_THREADS 1024                 // wide tier / fallback: one CTA per SM
+#define BM_WORDS 40960                  // wide tier: bitmap words in shared memory (1,310,720 distinct values)
+#define RK_THREADS_S 256                // small tier: value range < 65536 (counts of most samples): 8 CTAs per SM
+#define BM_WORDS_S 2048
 #define BM_GROUP 8                      // words per prefix entry
-#define BM_PRE (BM_WORDS / BM_GROUP)    // 5120 prefix entries
-#define BM_ITEMS ((BM_PRE + RK_THREADS - 1) / RK_THREADS)
 
 template <typename T>
 __device__ __forceinline__ bool to_ll(T v, long long& out);
@@ -49,7 +49,7 @@ __device__ __forceinline__ long long warp_max_ll(long long v) {
     return v;
 }
 
-// exclusive block scan of one int per thread (RK_THREADS threads); returns the exclusive prefix,
+// exclusive block scan of one int per thread (blockDim.x threads); returns the exclusive prefix,
 // *total receives the block total.  red: >= 33 ints of shared memory.
 __device__ __forceinline__ int block_excl_scan(int v, int* red, int* total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -71,27 +71,32 @@ __device__ __forceinline__ int block_excl_scan(int v, int* red, int* total) {
     return res;
 }
 
-template <typename T, typename RT>
-__global__ void __launch_bounds__(RK_THREADS, 1)
-rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t col0,
+// One CTA per sample column.  NTHR threads, BMW bitmap words: columns whose value range does not fit the bitmap are
+// appended to over_list (their list positions) for the next tier.  `cols` (optional) lists the positions to process.
+template <typename T, typename RT, int NTHR, int BMW>
+__global__ void __launch_bounds__(NTHR, (NTHR == RK_THREADS) ? 1 : 8)
+rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t col0, const int32_t* __restrict__ cols,
                     const int32_t* __restrict__ src_col, const int32_t* __restrict__ sample_id,
                     const int32_t* __restrict__ slot_of_sample, RT* __restrict__ ranks, int64_t rpad,
-                    int* max_distinct, int* flags, int32_t* fallback_list) {
+                    int* max_distinct, int* flags, int* over_count, int32_t* over_list) {
+    constexpr int BMP = BMW / BM_GROUP;                      // prefix entries
+    constexpr int BM_ITEMS = (BMP + NTHR - 1) / NTHR;
+    constexpr int RK_THREADS_L = NTHR;
     extern __shared__ uint32_t sm[];
-    uint32_t* bm = sm;                   // [BM_WORDS]
-    uint32_t* pre = sm + BM_WORDS;       // [BM_PRE]
-    int* red = (int*)(pre + BM_PRE);     // [40]
+    uint32_t* bm = sm;                   // [BMW]
+    uint32_t* pre = sm + BMW;            // [BMP]
+    int* red = (int*)(pre + BMP);        // [40]
     long long* redl = (long long*)(red + 40);  // [64]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t j = col0 + blockIdx.x;          // position in this rank's column list
+    const int64_t j = cols ? (int64_t)cols[blockIdx.x] : col0 + blockIdx.x;   // position in this rank's column list
     const int64_t s = sample_id[j];               // original sample index (slot lookup, fallback list)
     const T* __restrict__ col = data + ld * (int64_t)src_col[j];
 
     // phase 1: min / max / integrality
     long long mn = LLONG_MAX, mx = LLONG_MIN;
     int bad = 0;
-    for (int64_t g = tid; g < r; g += RK_THREADS) {
+    for (int64_t g = tid; g < r; g += RK_THREADS_L) {
         long long v;
         if (!to_ll<T>(col[g], v)) bad = 1;
         else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
@@ -101,8 +106,9 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     if (lane == 0) { redl[wid] = mn; redl[32 + wid] = mx; red[wid] = bad; }
     __syncthreads();
     if (wid == 0) {
-        mn = warp_min_ll(redl[lane]); mx = warp_max_ll(redl[32 + lane]);
-        bad = __any_sync(0xffffffffu, red[lane]);
+        const bool have = lane < (NTHR >> 5);
+        mn = warp_min_ll(have ? redl[lane] : LLONG_MAX); mx = warp_max_ll(have ? redl[32 + lane] : LLONG_MIN);
+        bad = __any_sync(0xffffffffu, have ? red[lane] : 0);
         if (lane == 0) { redl[0] = mn; redl[32] = mx; red[0] = bad; }
     }
     __syncthreads();
@@ -113,16 +119,16 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
         return;
     }
     const unsigned long long range = (unsigned long long)mx - (unsigned long long)mn;
-    if (range >= (unsigned long long)BM_WORDS * 32ull) {
-        if (tid == 0) { int k = atomicAdd(&flags[1], 1); fallback_list[k] = (int32_t)j; }
+    if (range >= (unsigned long long)BMW * 32ull) {   // next tier
+        if (tid == 0) { int k = atomicAdd(over_count, 1); over_list[k] = (int32_t)j; }
         return;
     }
     // phase 2: presence bitmap of (v - min)
     const int nwords = (int)(range >> 5) + 1;
     const int ngroups = (nwords + BM_GROUP - 1) / BM_GROUP;
-    for (int w = tid; w < ngroups * BM_GROUP; w += RK_THREADS) bm[w] = 0u;
+    for (int w = tid; w < ngroups * BM_GROUP; w += RK_THREADS_L) bm[w] = 0u;
     __syncthreads();
-    for (int64_t g = tid; g < r; g += RK_THREADS) {
+    for (int64_t g = tid; g < r; g += RK_THREADS_L) {
         long long v; to_ll<T>(col[g], v);
         const uint32_t k = (uint32_t)((unsigned long long)v - (unsigned long long)mn);
         atomicOr(&bm[k >> 5], 1u << (k & 31));
@@ -153,7 +159,7 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     // phase 4: dense rank lookup
     const int64_t slot = slot_of_sample[s];
     RT* __restrict__ out = ranks + slot * rpad;
-    for (int64_t g = tid; g < r; g += RK_THREADS) {
+    for (int64_t g = tid; g < r; g += RK_THREADS_L) {
         long long v; to_ll<T>(col[g], v);
         const uint32_t k = (uint32_t)((unsigned long long)v - (unsigned long long)mn);
         const uint32_t wq = k >> 5;
@@ -221,30 +227,51 @@ rank_fallback_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const in
     }
 }
 
-static size_t rank_smem_bytes() { return (size_t)(BM_WORDS + BM_PRE + 40) * 4 + 64 * 8 + 16; }
+static size_t rank_smem_bytes(int bmw) { return (size_t)(bmw + bmw / BM_GROUP + 40) * 4 + 64 * 8 + 16; }
+
+// tier 0 (small bitmap, 8 CTAs/SM) over list positions [col0, col0+ncols): overflow -> wide_list / flags[3]
+// tier 1 (wide bitmap, 1 CTA/SM) over wide_list: overflow -> fallback_list / flags[1]
+template <typename T, typename RT>
+static cudaError_t launch_rank_t(const void* data, int64_t r, int64_t ld, int64_t col0, int ncols, const int32_t* cols,
+                                 bool wide, const int32_t* src_col, const int32_t* sample_id,
+                                 const int32_t* slot_of_sample, void* ranks, int64_t rpad, int* max_distinct, int* flags,
+                                 int* over_count, int32_t* over_list, cudaStream_t st) {
+    if (ncols <= 0) return cudaSuccess;
+    cudaError_t e;
+    if (wide) {
+        const size_t smem = rank_smem_bytes(BM_WORDS);
+        e = cudaFuncSetAttribute(rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS><<<ncols, RK_THREADS, smem, st>>>(
+            (const T*)data, r, ld, col0, cols, src_col, sample_id, slot_of_sample, (RT*)ranks, rpad, max_distinct, flags,
+            over_count, over_list);
+    } else {
+        const size_t smem = rank_smem_bytes(BM_WORDS_S);
+        rank_columns_kernel<T, RT, RK_THREADS_S, BM_WORDS_S><<<ncols, RK_THREADS_S, smem, st>>>(
+            (const T*)data, r, ld, col0, cols, src_col, sample_id, slot_of_sample, (RT*)ranks, rpad, max_distinct, flags,
+            over_count, over_list);
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
-                                    const int32_t* src_col, const int32_t* sample_id,
+                                    const int32_t* cols, int wide, const int32_t* src_col, const int32_t* sample_id,
                                     const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,
-                                    int* max_distinct, int* flags, int32_t* fallback_list, cudaStream_t st) {
-    const size_t smem = rank_smem_bytes();
-    cudaError_t e;
-#define LAUNCH_RK2(T, RT)                                                                                        \
-    e = cudaFuncSetAttribute(rank_columns_kernel<T, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                              \
-    rank_columns_kernel<T, RT><<<ncols, RK_THREADS, smem, st>>>((const T*)data, r, ld, col0, src_col, sample_id, slot_of_sample, \
-                                                                (RT*)ranks, rpad, max_distinct, flags, fallback_list);
-#define LAUNCH_RK(T) if (rank_bytes == 2) { LAUNCH_RK2(T, uint16_t) } else { LAUNCH_RK2(T, uint32_t) }
+                                    int* max_distinct, int* flags, int* over_count, int32_t* over_list, cudaStream_t st) {
+#define LAUNCH_RK(T)                                                                                                   \
+    return rank_bytes == 2                                                                                             \
+               ? launch_rank_t<T, uint16_t>(data, r, ld, col0, ncols, cols, wide != 0, src_col, sample_id, slot_of_sample, \
+                                            ranks, rpad, max_distinct, flags, over_count, over_list, st)              \
+               : launch_rank_t<T, uint32_t>(data, r, ld, col0, ncols, cols, wide != 0, src_col, sample_id, slot_of_sample, \
+                                            ranks, rpad, max_distinct, flags, over_count, over_list, st);
     switch (dtype) {
-        case REO_I64: LAUNCH_RK(long long); break;
-        case REO_F64: LAUNCH_RK(double); break;
-        case REO_I32: LAUNCH_RK(int); break;
-        case REO_F32: LAUNCH_RK(float); break;
+        case REO_I64: LAUNCH_RK(long long)
+        case REO_F64: LAUNCH_RK(double)
+        case REO_I32: LAUNCH_RK(int)
+        case REO_F32: LAUNCH_RK(float)
         default: return cudaErrorInvalidValue;
     }
 #undef LAUNCH_RK
-#undef LAUNCH_RK2
-    return cudaGetLastError();
 }
 
 cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* fallback_list,
