@@ -324,13 +324,28 @@ def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
     thr = coracle.thresholds_for(gid, 2, 0.01)
     want = coracle.identify_degs(data, gid, 2, thr, 1.0, 0.05, ref, 128, 5, seed=7)
     ndev = min(torch.cuda.device_count(), 4)
-    with pkg.Reo(list(range(ndev)), seed=pkg.synth.TIE_SEED) as h:
-        out = h.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5)
-        check_full(out, want)
-        h.stage(data, gid, 2)
-        mask = np.arange(700) % 3 != 0
-        tab, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)
-        assert np.array_equal(h.tables(0, mask, thresholds=thr), tab)
+    for shard_min in ("0", None):   # "0": K1 (copy + rank + bit-planes) sharded over the devices as well
+        if shard_min is None:
+            os.environ.pop("REO_K1_SHARD_MIN", None)
+        else:
+            os.environ["REO_K1_SHARD_MIN"] = shard_min
+        try:
+            with pkg.Reo(list(range(ndev)), seed=pkg.synth.TIE_SEED) as h:
+                out = h.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5)
+                check_full(out, want)
+                h.stage(data, gid, 2)
+                mask = np.arange(700) % 3 != 0
+                tab, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)
+                assert np.array_equal(h.tables(0, mask, thresholds=thr), tab)
+                # float path and three levels through the sharded staging
+                fdata, fgroup = float_case(5, 300, 20, 25, 9)
+                flev, fgid = oracle.group_levels(fgroup)
+                fthr = coracle.thresholds_for(fgid, 3, 0.01)
+                fref = np.arange(300) % 4 == 0
+                fwant = coracle.identify_degs(fdata, fgid, 3, fthr, 1.0, 0.05, fref, 128, 5, seed=7)
+                check_full(h.identify_degs(fdata, fgid, 3, fref, 0.01, 1.0, 0.05, 128, 5), fwant)
+        finally:
+            os.environ.pop("REO_K1_SHARD_MIN", None)
 
 
 # ---- next to the path: pseudo-bulk, detection filters, subsetting ---------------
