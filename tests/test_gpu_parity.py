@@ -546,3 +546,14 @@ def test_c_driver_example(tmp_path):
     last = [l for l in out.stdout.splitlines() if l.startswith("genes")][0].split()
     called_up, planted_hit = int(last[7]), int(last[11])
     assert called_up > 100 and planted_hit > 100, out.stdout
+
+
+@pytest.mark.gpu
+def test_randomised_shape_sweep():
+    """120 random shapes / group layouts / dtypes / masks (scripts/fuzz_parity.py) against the C oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "120", "11"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
