@@ -24,6 +24,7 @@
 #ifndef REO_H
 #define REO_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -52,6 +53,10 @@ typedef enum { REO_I64 = 0, REO_F64 = 1, REO_I32 = 2, REO_F32 = 3 } reo_dtype;
 #define REO_FLAG_NONE 0u
 /* reo_identify_degs / reo_stage flags */
 #define REO_DATA_ON_DEVICE 1u /* `data` is a device pointer on the handle's first device */
+/* reo_identify_degs: result, updown and final_ref are page-locked host memory (reo_host_alloc, cudaHostAlloc or
+ * cudaHostRegister).  The device->host copies then land in them directly (no staging copy on the host) and
+ * overlap the last evaluation; the price: after a FAILED call they may hold intermediate values. */
+#define REO_OUT_PINNED 2u
 
 #define REO_MAX_ITER_LOG 256
 
@@ -96,6 +101,11 @@ int reo_set_collective(reo_handle_t h, int rank, int world, reo_allgather_fn fn,
  * with ncclAllGather on the handle's own stream (no host synchronisation, NVLink/NVSwitch transport). */
 int reo_comm_unique_id(void* out128);
 int reo_comm_init_rank(reo_handle_t h, int rank, int world, const void* id128);
+
+/* Page-locked host memory for REO_OUT_PINNED outputs (and for inputs: pinned inputs are copied to the device at
+ * full PCIe rate).  NULL on failure.  The memory outlives handles; free it with reo_host_free. */
+void* reo_host_alloc(size_t bytes);
+void reo_host_free(void* p);
 
 /* get_major_reo_lower_count(sample_size, pval_threshold), src:81-92.  Host arithmetic. */
 int reo_threshold(int sample_size, double pval_reo);

@@ -20,12 +20,13 @@ REO_ERR_STATE = -8
 
 REO_I64, REO_F64, REO_I32, REO_F32 = 0, 1, 2, 3
 REO_DATA_ON_DEVICE = 1
+REO_OUT_PINNED = 2
 REO_MAX_ITER_LOG = 256
 
 # every symbol include/reo.h declares
 SYMBOLS = [
     "reo_version", "reo_create", "reo_destroy", "reo_last_error", "reo_set_collective", "reo_comm_unique_id",
-    "reo_comm_init_rank", "reo_threshold",
+    "reo_comm_init_rank", "reo_host_alloc", "reo_host_free", "reo_threshold",
     "reo_identify_degs", "reo_stage", "reo_stage_info", "reo_pair_counts", "reo_tables", "reo_tables_delta",
     "reo_mccullagh", "reo_empirical_null", "reo_bh", "reo_sort_f64", "reo_pseudobulk", "reo_detect_counts", "reo_subset",
 ]
@@ -80,6 +81,10 @@ def load():
     L.reo_comm_unique_id.argtypes = [vp]
     L.reo_comm_init_rank.restype = C.c_int
     L.reo_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.reo_host_alloc.restype = vp
+    L.reo_host_alloc.argtypes = [C.c_size_t]
+    L.reo_host_free.restype = None
+    L.reo_host_free.argtypes = [vp]
     L.reo_threshold.restype = C.c_int
     L.reo_threshold.argtypes = [C.c_int, dbl]
     L.reo_identify_degs.restype = C.c_int

@@ -24,6 +24,40 @@ HEADER = ["pval", "padj", "n11", "n12", "n13", "n21", "n22", "n23", "n31", "n32"
           "Δ1", "Δ2", "se", "z1", "up_down"]  # src:665
 
 
+class _PinnedBlock:
+    """A page-locked host block from reo_host_alloc; numpy arrays built on it keep it alive through .base, and
+    it goes back to the pool (not to the driver: cudaFreeHost costs more than the copy it saves) when dropped."""
+
+    __slots__ = ("ptr", "nbytes", "__array_interface__")
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__array_interface__ = {"data": (ptr, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_pool.setdefault(self.nbytes, []).append(self.ptr)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+_pinned_pool: dict = {}
+_PINNED_ROUND = 1 << 16
+
+
+def _pinned_empty(shape, dtype):
+    """np.empty(shape, dtype) in page-locked memory (size rounded up to 64 KiB so blocks recycle across calls)."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    nbytes = max((n + _PINNED_ROUND - 1) // _PINNED_ROUND, 1) * _PINNED_ROUND
+    free = _pinned_pool.get(nbytes)
+    ptr = free.pop() if free else L.load().reo_host_alloc(nbytes)
+    if not ptr:
+        raise MemoryError(f"reo_host_alloc({nbytes}) failed")
+    block = _PinnedBlock(ptr, nbytes)
+    return np.asarray(block)[:n].view(dt).reshape(shape)
+
+
 class ReoError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libreo_cuda error {code}: {msg}")
@@ -175,9 +209,11 @@ class Reo:
             raise ValueError("DimensionMismatch: 'ref_gene' and 'data' do not have compatiable sizes")
         K = 1 if gnum == 2 else max(int(gnum), 1)
         thr = None if thresholds is None else np.asfortranarray(np.asarray(thresholds, dtype=np.int32))
-        result = np.empty((K, 15, r), dtype=np.float64)  # column-major r x 15 per k, filled by the library
-        updown = np.empty((K, r), dtype=np.int8)
-        final_ref = np.empty((K, r), dtype=np.uint8)
+        # outputs live in recycled page-locked blocks: the library copies device->host straight into them
+        result = _pinned_empty((K, 15, r), np.float64)   # column-major r x 15 per k, filled by the library
+        updown = _pinned_empty((K, r), np.int8)
+        final_ref = _pinned_empty((K, r), np.uint8)
+        flags |= L.REO_OUT_PINNED
         iters = np.zeros(K, dtype=np.int32)
         st = L.ReoStats()
         rc = self._lib.reo_identify_degs(self._h, p, dt, r, c, ld, _ptr(gid), int(gnum), _ptr(thr), float(pval_reo),

@@ -100,6 +100,7 @@ struct ReoDev {
     int32_t* h_counts = nullptr;  // pinned
     uint8_t* h_out = nullptr;     // pinned staging for results (grow-only)
     size_t h_out_cap = 0;
+    bool early_pending = false;   // a copy of result columns 2..14 is in flight on st_copy (ev[7] marks its end)
     int table_rows = 0;           // rows allocated in `table`
     std::vector<cudaEvent_t> pev; // event pairs bracketing every pair-kernel launch of the current call
     int n_pev = 0;
@@ -573,16 +574,31 @@ int allgather_tables(reo_handle_t h, ReoDev& D) {
 
 // One evaluation of src:402-417 on the current tables: McCullagh per gene, sort + trimmed std, empirical-null p,
 // BH, new mask, symmetric difference, and the three counters the host decides on (read back into pinned memory).
+// src:402-406: tables -> result columns 2..14.  Those 13 columns are final for this evaluation, so their
+// device->host copy starts on the copy stream at once and overlaps the rest of the sequence (early_dst: the host
+// image of `result` for this level, pinned).
+int enqueue_mcc(reo_handle_t h, ReoDev& D, int64_t r, double* early_dst) {
+    if (D.early_pending) CK(cudaStreamWaitEvent(D.st, D.ev[7], 0));   // the previous copy still reads `result`
+    CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
+    if (early_dst) {
+        CK(cudaEventRecord(D.ev[6], D.st));
+        CK(cudaStreamWaitEvent(D.st_copy, D.ev[6], 0));
+        CK(cudaMemcpyAsync(early_dst + 2 * r, D.result.p + 2 * r, (size_t)r * 13 * sizeof(double), cudaMemcpyDeviceToHost, D.st_copy));
+        CK(cudaEventRecord(D.ev[7], D.st_copy));
+        D.early_pending = true;
+    }
+    return REO_OK;
+}
+
 int enqueue_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double padj_deg, uint8_t* mask_cur,
                  uint8_t* mask_new) {
-    CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));                                   // src:402-406
     CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, D.perm.p, D.sortws, D.st));     // src:409
     CKL(reo_launch_trimmed_std(D.sorted.p, r, D.se.p, D.std_ws.p, D.st));                               // src:411
-    CKL(reo_launch_null_pvals(D.result.p + (size_t)r * 11, r, D.se.p, D.result.p, D.st));               // src:412
-    // src:413: the ascending order of p follows from the sorted d1 (p decreases with |d1|): no second sort
-    CKL(reo_launch_p_order(D.sorted.p, D.perm.p, r, D.result.p, D.sorted_p.p, D.perm2.p, D.st));
-    CKL(reo_launch_bh(D.sorted_p.p, D.perm2.p, r, D.result.p + r, D.sorted.p /* free after p_order: scratch */, D.st));
-    CKL(reo_launch_inds(D.result.p, D.result.p + r, r, pval_deg, padj_deg, mask_new, D.st));            // src:417
+    // src:412-413: p-values from the sorted d1; their ascending order follows from it too (p decreases with |d1|):
+    // no second sort.  BH also writes the new reference mask (src:417).
+    CKL(reo_launch_p_order(D.sorted.p, D.perm.p, r, D.result.p, D.se.p, D.sorted_p.p, D.perm2.p, D.st));
+    CKL(reo_launch_bh(D.sorted_p.p, D.perm2.p, r, D.result.p + r, D.sorted.p /* free after p_order: scratch */,
+                      mask_new, pval_deg, padj_deg, D.st));
     CKL(reo_launch_mask_diff(r, mask_cur, mask_new, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
     CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
     return REO_OK;
@@ -592,13 +608,16 @@ void drop_eval_graphs(ReoDev& D) {
     for (auto& e : D.eval_exec) { if (e) cudaGraphExecDestroy(e); e = nullptr; }
 }
 
-// Launch the evaluation sequence as one CUDA graph (11 small kernels: the launch gaps otherwise dominate).
+// Launch the evaluation sequence: the table statistics first, then the remaining 7 small kernels as one CUDA graph
+// (their launch gaps otherwise dominate).
 int run_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double padj_deg, uint8_t* mask_cur,
-             uint8_t* mask_new) {
-    h->kernel_launches += 11;  // mccullagh, sort x3, std x2, pvals, p_order, bh, inds, diff
+             uint8_t* mask_new, double* early_dst) {
+    h->kernel_launches += 8;  // mccullagh, sort x2, std, p_order, bh x2, diff
     static const bool no_graph = getenv("REO_NO_GRAPH") != nullptr;
+    CK(reo_sort_reserve(D.sortws, r, D.st));
+    const int rc0 = enqueue_mcc(h, D, r, early_dst);
+    if (rc0 != REO_OK) return rc0;
     if (debug_sync() || no_graph) return enqueue_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new);
-    CK(reo_sort_reserve(D.sortws, r));
     const std::vector<const void*> key = {D.table.p, D.result.p, D.sorted.p, D.perm.p, D.sorted_p.p, D.perm2.p, D.se.p,
                                           D.counts.p, D.changed_gene.p, D.changed_sign.p, D.sortws.keys, D.std_ws.p,
                                           D.mask_a.p, D.mask_b.p, D.h_counts};
@@ -641,6 +660,13 @@ int run_multi(reo_handle_t parent, F f) {
 extern "C" {
 
 int reo_version(void) { return REO_VERSION; }
+
+void* reo_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void reo_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 const char* reo_last_error(reo_handle_t h) {
     if (h) return h->err.c_str();
@@ -765,6 +791,7 @@ int reo_destroy(reo_handle_t h) {
         if (D.sortws.keys) cudaFree(D.sortws.keys);
         if (D.sortws.idx) cudaFree(D.sortws.idx);
         if (D.sortws.pos) cudaFree(D.sortws.pos);
+        if (D.sortws.cnt) cudaFree(D.sortws.cnt);
         if (D.h_counts) cudaFreeHost(D.h_counts);
         if (D.h_out) cudaFreeHost(D.h_out);
         D.std_ws.release();
@@ -957,13 +984,13 @@ int reo_bh(reo_handle_t h, const double* p, int64_t n, double* padj) {
     ReoDev& D = h->devs[0];
     if (!p || !padj || n < 1) return fail(h, REO_ERR_ARG, "reo_bh: bad argument");
     CK(cudaSetDevice(D.dev));
-    CK(D.small_d.ensure((size_t)3 * n));
+    CK(D.small_d.ensure((size_t)4 * n + n / 1024 + 2));
     CK(D.perm.ensure(n));
-    double* d_x = D.small_d.p; double* d_s = d_x + n; double* d_q = d_s + n;
+    double* d_x = D.small_d.p; double* d_s = d_x + n; double* d_q = d_s + n; double* d_w = d_q + n;
     CK(cudaMemcpyAsync(d_x, p, n * 8, cudaMemcpyHostToDevice, D.st));
     if (n > 1) {
         CKL(reo_launch_sort_f64(d_x, n, d_s, D.perm.p, D.sortws, D.st));
-        CKL(reo_launch_bh(d_s, D.perm.p, n, d_q, d_x /* input already sorted into d_s: scratch */, D.st));
+        CKL(reo_launch_bh(d_s, D.perm.p, n, d_q, d_w, nullptr, 0.0, 0.0, D.st));
     } else {
         d_q = d_x;
     }
@@ -1073,7 +1100,8 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             double* ro = result; int8_t* uo = updown;
             if (i > 0) { res[i].resize((size_t)K * r * 15); ud[i].resize((size_t)K * r); ro = res[i].data(); uo = ud[i].data(); }
             return reo_identify_degs(s, data, dtype, r, c, ld, group_id, gnum, thresholds, pval_reo, pval_deg, padj_deg,
-                                     ref_mask, n_iter, n_conv, flags, ro, uo, i == 0 ? final_ref : nullptr,
+                                     ref_mask, n_iter, n_conv, i == 0 ? flags : (flags & ~REO_OUT_PINNED), ro, uo,
+                                     i == 0 ? final_ref : nullptr,
                                      i == 0 ? iters_done : nullptr, &sts[i]);
         });
         if (rc == REO_OK && stats) {
@@ -1106,18 +1134,25 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     const ReoStaged& S = D.S;
     const int K = gnum == 2 ? 1 : gnum;
     CK(D.result.ensure((size_t)r * 15));
-    CK(D.sorted.ensure(r)); CK(D.sorted_p.ensure(r)); CK(D.perm.ensure(r)); CK(D.perm2.ensure(r)); CK(D.se.ensure(1)); CK(D.updown.ensure(r));
+    CK(D.sorted.ensure(r + r / 1024 + 2)); CK(D.sorted_p.ensure(r)); CK(D.perm.ensure(r)); CK(D.perm2.ensure(r)); CK(D.se.ensure(1)); CK(D.updown.ensure(r));
     if ((rc = ensure_std_ws(h, D))) return rc;
     reo_stats st_local;
     memset(&st_local, 0, sizeof(st_local));
     double ms_pairs = 0.0;
-    // results are assembled in a pinned staging buffer so that caller outputs stay untouched on failure
+    // results are assembled in a pinned staging buffer so that caller outputs stay untouched on failure; with
+    // REO_OUT_PINNED the caller's own (page-locked) buffers take that role
+    const bool direct = (flags & REO_OUT_PINNED) != 0;
     const size_t res_bytes = (size_t)K * r * 15 * sizeof(double);
     if ((rc = ensure_h_out(h, D, res_bytes + 2 * (size_t)K * r + 64))) return rc;
-    double* res_host = reinterpret_cast<double*>(D.h_out);
-    int8_t* ud_host = reinterpret_cast<int8_t*>(D.h_out + res_bytes);
-    uint8_t* fr_host = D.h_out + res_bytes + (size_t)K * r;
+    double* res_host = direct ? result : reinterpret_cast<double*>(D.h_out);
+    int8_t* ud_host = direct ? updown : reinterpret_cast<int8_t*>(D.h_out + res_bytes);
+    uint8_t* fr_host = (direct && final_ref) ? final_ref : D.h_out + res_bytes + (size_t)K * r;
     std::vector<int32_t> it_host(K, 0);
+    D.early_pending = false;
+    struct CopyGuard {   // no copy into host memory may outlive the call, whatever the exit path
+        ReoDev& D;
+        ~CopyGuard() { if (D.early_pending) { cudaStreamSynchronize(D.st_copy); D.early_pending = false; } }
+    } copy_guard{D};
 
     for (int k = 0; k < K; ++k) {
         LevelPlan P = make_plan(S, k, thresholds, pval_reo);
@@ -1136,7 +1171,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             if ((rc = allgather_tables(h, D))) return rc;
             static const bool timing = getenv("REO_TIMING") != nullptr;
             if (timing) CK(cudaEventRecord(D.ev[3], D.st));
-            if ((rc = run_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new))) return rc;
+            if ((rc = run_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new, res_host + (size_t)k * r * 15))) return rc;
             if (timing) {
                 CK(cudaEventRecord(D.ev[4], D.st));
                 CK(cudaEventSynchronize(D.ev[4]));
@@ -1167,10 +1202,13 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         if (n_eval == 0) CK(cudaMemsetAsync(D.result.p, 0, (size_t)r * 15 * sizeof(double), D.st));
         CKL(reo_launch_updown(D.result.p, r, pval_deg, padj_deg, D.updown.p, D.st));
         h->kernel_launches++;
-        CK(cudaMemcpyAsync(res_host + (size_t)k * r * 15, D.result.p, (size_t)r * 15 * 8, cudaMemcpyDeviceToHost, D.st));
+        // columns 2..14 of the last evaluation are already on their way (enqueue_mcc): only pval and padj are left
+        const size_t tail_cols = D.early_pending ? 2 : 15;
+        CK(cudaMemcpyAsync(res_host + (size_t)k * r * 15, D.result.p, (size_t)r * tail_cols * 8, cudaMemcpyDeviceToHost, D.st));
         CK(cudaMemcpyAsync(ud_host + (size_t)k * r, D.updown.p, r, cudaMemcpyDeviceToHost, D.st));
         CK(cudaMemcpyAsync(fr_host + (size_t)k * r, mask_cur, r, cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
+        if (D.early_pending) { CK(cudaStreamSynchronize(D.st_copy)); D.early_pending = false; }
         it_host[k] = n_eval;
         st_local.iters_done = n_eval; st_local.converged = converged;
     }
@@ -1186,9 +1224,11 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         cudaEventElapsedTime(&ms, D.pev[2 * i], D.pev[2 * i + 1]);
         ms_pairs += ms;
     }
-    memcpy(result, res_host, res_bytes);
-    memcpy(updown, ud_host, (size_t)K * r);
-    if (final_ref) memcpy(final_ref, fr_host, (size_t)K * r);
+    if (!direct) {
+        memcpy(result, res_host, res_bytes);
+        memcpy(updown, ud_host, (size_t)K * r);
+        if (final_ref) memcpy(final_ref, fr_host, (size_t)K * r);
+    }
     if (iters_done) memcpy(iters_done, it_host.data(), K * sizeof(int32_t));
     if (stats) {
         st_local.rank_bits = S.B; st_local.sample_words = S.W; st_local.compares = h->compares;

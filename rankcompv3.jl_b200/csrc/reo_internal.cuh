@@ -130,16 +130,18 @@ struct ReoSortWs {  // workspace for reo_sort
     unsigned long long* keys = nullptr;  // chunk-sorted keys
     uint32_t* idx = nullptr;
     int32_t* pos = nullptr;
+    unsigned int* cnt = nullptr;         // per-chunk arrival counters (zero between launches)
     int64_t cap = 0;
 };
-cudaError_t reo_sort_reserve(ReoSortWs& ws, int64_t n);
+cudaError_t reo_sort_reserve(ReoSortWs& ws, int64_t n, cudaStream_t st);
 cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int32_t* perm, ReoSortWs& ws,
                                 cudaStream_t st);
 cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* leaf_ws, cudaStream_t st);
 cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se, double* pval, cudaStream_t st);
-cudaError_t reo_launch_p_order(const double* sorted, const int32_t* perm1, int64_t n, const double* pval,
+cudaError_t reo_launch_p_order(const double* sorted, const int32_t* perm1, int64_t n, double* pval, const double* se,
                                double* sorted_p, int32_t* perm2, cudaStream_t st);
 cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* ws,
+                          uint8_t* mask_new /*nullable: also write src:417's inds*/, double pval_deg, double padj_deg,
                           cudaStream_t st);
 // inds = !(p<=pd && q<=qd) (src:417)
 cudaError_t reo_launch_inds(const double* pval, const double* padj, int64_t r, double pval_deg, double padj_deg,

@@ -183,23 +183,41 @@ sort_chunks_kernel(const double* __restrict__ x, int64_t n, unsigned long long* 
     keys[g] = k; idx[g] = i; pos[g] = t;
 }
 
-// grid (A, B): every element of chunk A counts the elements of chunk B below it (binary search in shared memory)
+// grid (A, B): every element of chunk A counts the elements of chunk B below it (binary search in shared memory);
+// the last CTA to finish a chunk A scatters that chunk to its final positions.
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_cross_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx, int32_t* __restrict__ pos) {
+sort_cross_kernel(const double* __restrict__ x, const unsigned long long* __restrict__ keys,
+                  const uint32_t* __restrict__ idx, int32_t* __restrict__ pos, unsigned int* __restrict__ cnt,
+                  double* __restrict__ sorted, int32_t* __restrict__ perm) {
     __shared__ unsigned long long sk[SORT_CHUNK];
     __shared__ uint32_t si[SORT_CHUNK];
+    __shared__ int last;
     const int A = blockIdx.x, B = blockIdx.y, t = threadIdx.x;
     if (A == B) return;
     sk[t] = keys[(int64_t)B * SORT_CHUNK + t]; si[t] = idx[(int64_t)B * SORT_CHUNK + t];
     const unsigned long long ke = keys[(int64_t)A * SORT_CHUNK + t];
     const uint32_t ie = idx[(int64_t)A * SORT_CHUNK + t];
     __syncthreads();
-    if (ie == 0xffffffffu) return;
-    int a = 0, b = SORT_CHUNK;
-    while (a < b) { const int m = (a + b) >> 1; if (kv_less(sk[m], si[m], ke, ie)) a = m + 1; else b = m; }
-    if (a) atomicAdd(&pos[(int64_t)A * SORT_CHUNK + t], a);
+    if (ie != 0xffffffffu) {
+        int a = 0, b = SORT_CHUNK;
+        while (a < b) { const int m = (a + b) >> 1; if (kv_less(sk[m], si[m], ke, ie)) a = m + 1; else b = m; }
+        if (a) atomicAdd(&pos[(int64_t)A * SORT_CHUNK + t], a);
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        last = (atomicAdd(&cnt[A], 1u) == gridDim.y - 2);    // gridDim.y - 1 CTAs work on chunk A
+        if (last) cnt[A] = 0u;
+    }
+    __syncthreads();
+    if (!last || ie == 0xffffffffu) return;
+    __threadfence();
+    const int32_t p = *(reinterpret_cast<volatile int32_t*>(pos) + (int64_t)A * SORT_CHUNK + t);
+    sorted[p] = x[ie];
+    if (perm) perm[p] = (int32_t)ie;
 }
 
+// single-chunk case: the chunk order is the final order
 __global__ void sort_scatter_kernel(const double* __restrict__ x, int64_t total, const uint32_t* __restrict__ idx,
                                     const int32_t* __restrict__ pos, double* __restrict__ sorted,
                                     int32_t* __restrict__ perm) {
@@ -213,19 +231,24 @@ __global__ void sort_scatter_kernel(const double* __restrict__ x, int64_t total,
 }
 
 // make sure the workspace holds n elements (allocation must not happen while a stream is being captured)
-cudaError_t reo_sort_reserve(ReoSortWs& ws, int64_t n) {
+cudaError_t reo_sort_reserve(ReoSortWs& ws, int64_t n, cudaStream_t st) {
     const int nchunks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
     const int64_t need = (int64_t)nchunks * SORT_CHUNK;
     if (ws.cap < need) {
         if (ws.keys) cudaFree(ws.keys);
         if (ws.idx) cudaFree(ws.idx);
         if (ws.pos) cudaFree(ws.pos);
-        ws.keys = nullptr; ws.idx = nullptr; ws.pos = nullptr; ws.cap = 0;
+        if (ws.cnt) cudaFree(ws.cnt);
+        ws.keys = nullptr; ws.idx = nullptr; ws.pos = nullptr; ws.cnt = nullptr; ws.cap = 0;
         cudaError_t e = cudaMalloc(&ws.keys, need * sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
         e = cudaMalloc(&ws.idx, need * sizeof(uint32_t));
         if (e != cudaSuccess) return e;
         e = cudaMalloc(&ws.pos, need * sizeof(int32_t));
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&ws.cnt, nchunks * sizeof(unsigned int));
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(ws.cnt, 0, nchunks * sizeof(unsigned int), st);   // every launch leaves the counters at zero
         if (e != cudaSuccess) return e;
         ws.cap = need;
     }
@@ -237,25 +260,15 @@ cudaError_t reo_launch_sort_f64(const double* x, int64_t n, double* sorted, int3
     if (n <= 0) return cudaSuccess;
     const int nchunks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
     const int64_t need = (int64_t)nchunks * SORT_CHUNK;
-    if (ws.cap < need) {
-        if (ws.keys) cudaFree(ws.keys);
-        if (ws.idx) cudaFree(ws.idx);
-        if (ws.pos) cudaFree(ws.pos);
-        ws.keys = nullptr; ws.idx = nullptr; ws.pos = nullptr; ws.cap = 0;
-        cudaError_t e = cudaMalloc(&ws.keys, need * sizeof(unsigned long long));
-        if (e != cudaSuccess) return e;
-        e = cudaMalloc(&ws.idx, need * sizeof(uint32_t));
-        if (e != cudaSuccess) return e;
-        e = cudaMalloc(&ws.pos, need * sizeof(int32_t));
-        if (e != cudaSuccess) return e;
-        ws.cap = need;
-    }
+    const cudaError_t e = reo_sort_reserve(ws, n, st);
+    if (e != cudaSuccess) return e;
     sort_chunks_kernel<<<nchunks, SORT_THREADS, 0, st>>>(x, n, ws.keys, ws.idx, ws.pos);
     if (nchunks > 1) {
         dim3 grid(nchunks, nchunks);
-        sort_cross_kernel<<<grid, SORT_THREADS, 0, st>>>(ws.keys, ws.idx, ws.pos);
+        sort_cross_kernel<<<grid, SORT_THREADS, 0, st>>>(x, ws.keys, ws.idx, ws.pos, ws.cnt, sorted, perm);
+    } else {
+        sort_scatter_kernel<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(x, need, ws.idx, ws.pos, sorted, perm);
     }
-    sort_scatter_kernel<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(x, need, ws.idx, ws.pos, sorted, perm);
     return cudaGetLastError();
 }
 
@@ -307,64 +320,75 @@ __device__ int std_leaf_bounds(int64_t lo0, int64_t hi0, int want, int64_t* lo_o
     return nl;
 }
 
-// PASS 0: leaf sums of x -> mean.  PASS 1: leaf sums of (x-mean)^2 -> se.  One warp per leaf: lane l holds the
-// values lo + 32k + l in registers (32 coalesced loads in flight), then every lane forms the SAME strictly
-// left-to-right sum by pulling value after value out of its owner with a shuffle; the last CTA to finish combines
-// the leaves in tree order.  ws: [0..255] leaf sums, [256] mean.
-template <int PASS>
+// One warp (CTA of 32) per leaf.  The leaf's values are staged in shared memory (coalesced) and then summed
+// strictly left to right -- f(a1) + f(a2), then + f(a_i) -- by every lane redundantly (broadcast LDS.128, so the
+// serial DADD chain is the only dependency).  Pass 0 sums x; the last CTA to arrive combines the leaves in tree
+// order into the mean and releases the others (all CTAs of this small grid are co-resident: nleaf <= 256 warps
+// on 148 SMs); pass 1 sums (x-mean)^2 and the last CTA combines again into se.  ws: [0..255] leaf sums,
+// [256] mean, then 3 uint32 (arrivals of pass 0, arrivals of pass 1, release flag), all zero between launches.
+__device__ __forceinline__ double std_seq_sum(const double* vals, int cnt) {
+    double v = vals[0];
+    int i = 1;
+    if (cnt > 1) { v = v + vals[1]; i = 2; }               // pairs from here on are 16-byte aligned
+    const double2* v2 = reinterpret_cast<const double2*>(vals);
+#pragma unroll 8
+    for (; i + 1 < cnt; i += 2) {
+        const double2 t = v2[i >> 1];
+        v = v + t.x;
+        v = v + t.y;
+    }
+    if (i < cnt) v = v + vals[i];
+    return v;
+}
+
 __global__ void __launch_bounds__(32)
-std_leaf_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ ws,
-                unsigned int* __restrict__ done, double* __restrict__ se_out) {
+std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ ws,
+           double* __restrict__ se_out) {
+    __shared__ __align__(16) double vals[1024];
     __shared__ double buf[STD_MAX_LEAVES];
     __shared__ StdFrame frames[64];
     __shared__ int64_t b_lo, b_hi;
-    __shared__ int last;
+    __shared__ double mean_s;
+    unsigned int* sync = reinterpret_cast<unsigned int*>(ws + STD_MAX_LEAVES + 1);
     const int lane = threadIdx.x;
     if (lane == 0) std_leaf_bounds(lo0, hi0, blockIdx.x, &b_lo, &b_hi, frames);
     __syncwarp();
-    const int64_t lo = b_lo, hi = b_hi;
-    const int cnt = (int)(hi - lo + 1);                    // <= 1024
-    const double mean = PASS ? ws[STD_MAX_LEAVES] : 0.0;
-    double reg[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        const int i = k * 32 + lane;
-        double xv = 0.0;
-        if (i < cnt) { xv = sorted[lo + i]; if (PASS) xv = (xv - mean) * (xv - mean); }
-        reg[k] = xv;
-    }
-    double v = 0.0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        if (k * 32 + 32 <= cnt) {                           // warp-uniform: a full row of 32
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const double xv = __shfl_sync(0xffffffffu, reg[k], l);
-                v = (k == 0 && l == 0) ? xv : v + xv;       // f(a1) + f(a2), then + f(a_i) left to right
+    const int64_t lo = b_lo, hi = b_hi, m_all = hi0 - lo0 + 1;
+    const int cnt = (int)(hi - lo + 1);                    // 1..1024
+    for (int i = lane; i < cnt; i += 32) vals[i] = sorted[lo + i];
+    __syncwarp();
+    const volatile double* vw = ws;
+    for (int pass = 0; pass < 2; ++pass) {
+        const double v = std_seq_sum(vals, cnt);
+        if (lane == 0) {
+            ws[blockIdx.x] = v;
+            __threadfence();
+            const bool last = (atomicAdd(&sync[pass], 1u) == gridDim.x - 1);
+            if (last) {
+                __threadfence();
+                for (int l = 0; l < (int)gridDim.x; ++l) buf[l] = vw[l];
+                const double tot = std_combine(lo0, hi0, buf, frames);
+                if (pass == 0) {
+                    ws[STD_MAX_LEAVES] = tot / (double)m_all;
+                    __threadfence();
+                    atomicExch(&sync[2], 1u);              // release the other leaves
+                } else {
+                    *se_out = sqrt(tot / (double)(m_all - 1));
+                    sync[0] = 0u; sync[1] = 0u; sync[2] = 0u;   // everybody is past the flag by now
+                }
             }
-        } else if (k * 32 < cnt) {
-            const int m = cnt - k * 32;
-            for (int l = 0; l < m; ++l) {
-                const double xv = __shfl_sync(0xffffffffu, reg[k], l);
-                v = (k == 0 && l == 0) ? xv : v + xv;
+            if (pass == 0) {
+                while (atomicAdd(&sync[2], 0u) == 0u) { }
+                __threadfence();
+                mean_s = vw[STD_MAX_LEAVES];
             }
         }
-    }
-    if (lane == 0) {
-        ws[blockIdx.x] = v;
-        __threadfence();
-        last = (atomicAdd(done, 1u) == gridDim.x - 1);
-    }
-    __syncwarp();
-    if (last && lane == 0) {
-        __threadfence();
-        const volatile double* vw = ws;
-        for (int l = 0; l < (int)gridDim.x; ++l) buf[l] = vw[l];
-        const double tot = std_combine(lo0, hi0, buf, frames);
-        const int64_t m = hi0 - lo0 + 1;
-        if (PASS == 0) ws[STD_MAX_LEAVES] = tot / (double)m;
-        else *se_out = sqrt(tot / (double)(m - 1));
-        *done = 0u;
+        __syncwarp();
+        if (pass == 0) {
+            const double mean = mean_s;
+            for (int i = lane; i < cnt; i += 32) { const double d = vals[i] - mean; vals[i] = d * d; }
+            __syncwarp();
+        }
     }
 }
 
@@ -380,24 +404,24 @@ cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_o
     if (lo < 1 || hi > n || hi < lo || !ws) return cudaErrorInvalidValue;
     const int nleaf = std_count_leaves(lo - 1, hi - 1);
     if (nleaf > STD_MAX_LEAVES) return cudaErrorInvalidValue;
-    unsigned int* done = reinterpret_cast<unsigned int*>(ws + STD_MAX_LEAVES + 1);
-    std_leaf_kernel<0><<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws, done, se_out);
-    std_leaf_kernel<1><<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws, done, se_out);
+    std_kernel<<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws, se_out);
     return cudaGetLastError();
 }
 
-// src:412: pvalue(Normal(0, se), d1; tail = :both) -> result column 0
-__global__ void null_pvals_kernel(const double* __restrict__ d1, int64_t n, const double* __restrict__ se_p,
-                                  double* __restrict__ pval) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double se = *se_p, d = d1[i];
+// src:412: pvalue(Normal(0, se), d1; tail = :both)
+__device__ __forceinline__ double null_p(double d, double se) {
     double z;
     if (se == 0.0) z = (d == 0.0) ? 0.0 : copysign(INFINITY, d);
     else z = (d - 0.0) / se;
     const double cdf = erfc(-z * REO_INVSQRT2) / 2, ccdf = erfc(z * REO_INVSQRT2) / 2;
     const double p = 2 * (cdf < ccdf ? cdf : ccdf);
-    pval[i] = p < 1.0 ? p : 1.0;
+    return p < 1.0 ? p : 1.0;
+}
+__global__ void null_pvals_kernel(const double* __restrict__ d1, int64_t n, const double* __restrict__ se_p,
+                                  double* __restrict__ pval) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pval[i] = null_p(d1[i], *se_p);
 }
 cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se, double* pval, cudaStream_t st) {
     null_pvals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d1, n, se, pval);
@@ -408,11 +432,13 @@ cudaError_t reo_launch_null_pvals(const double* d1, int64_t n, const double* se,
 // Ascending order of the empirical-null p-values WITHOUT a second sort: p is a non-increasing function of |d1|,
 // so it is the merge, by descending magnitude, of the negative run of the sorted d1 (already descending in
 // magnitude) with the reversed non-negative run.  Ties in p get equal adjusted values whatever their order.
-// sorted: d1 ascending, perm1: its permutation.  Outputs sorted_p (ascending) and perm2.
+// sorted: d1 ascending, perm1: its permutation.  Outputs sorted_p (ascending) and perm2.  With se_p the p-value
+// of every gene is computed here from its sorted d1 (bit-identical to d1[g]) and also stored to pval[g] (src:412,
+// 415); without it pval is an input.
 // ------------------------------------------------------------------------------------------------
 __global__ void p_order_kernel(const double* __restrict__ sorted, const int32_t* __restrict__ perm1, int64_t n,
-                               const double* __restrict__ pval, double* __restrict__ sorted_p,
-                               int32_t* __restrict__ perm2) {
+                               double* __restrict__ pval, const double* __restrict__ se_p,
+                               double* __restrict__ sorted_p, int32_t* __restrict__ perm2) {
     __shared__ int64_t nv_s, m_s;
     if (threadIdx.x == 0) {
         // NaNs sort last (Julia isless): they keep their places and the merge runs over the first nv elements
@@ -446,62 +472,77 @@ __global__ void p_order_kernel(const double* __restrict__ sorted, const int32_t*
         pos = (nv - 1 - e) + a;
     }
     const int32_t g = perm1[e];
-    sorted_p[pos] = pval[g];
+    double p;
+    if (se_p) { p = null_p(v, *se_p); pval[g] = p; }
+    else p = pval[g];
+    sorted_p[pos] = p;
     perm2[pos] = g;
 }
-cudaError_t reo_launch_p_order(const double* sorted, const int32_t* perm1, int64_t n, const double* pval,
+cudaError_t reo_launch_p_order(const double* sorted, const int32_t* perm1, int64_t n, double* pval, const double* se,
                                double* sorted_p, int32_t* perm2, cudaStream_t st) {
-    p_order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted, perm1, n, pval, sorted_p, perm2);
+    p_order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted, perm1, n, pval, se, sorted_p, perm2);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // Benjamini-Hochberg, src:413 (MultipleTesting 0.5.1): q_(m) = p_(m) * (n/m), reverse running
-// minimum, min(.,1), un-permute.  One CTA; suffix-min by per-thread chunks + block scan.
+// minimum, min(.,1), un-permute.
 // ------------------------------------------------------------------------------------------------
 #define BH_THREADS 1024
-// q_(m) = min(q_(m+1), p_(m) * (n/m)): reverse running minimum.  Each warp owns a contiguous segment (coalesced
-// rows of 32), scans it from the top with shuffles (partial result parked in `scratch`), then adds the minimum of
-// the warps to its right.  One barrier.
+// q_(m) = min(q_(m+1), p_(m) * (n/m)): reverse running minimum (min is exact, so it may be formed in any order).
+// bh_scan: every CTA forms the suffix minimum inside its 1024 elements (scratch) and the minimum of the whole
+// segment (tot[]).  bh_finish: adds the minimum of the segments to the right, clamps, un-permutes and, when asked,
+// writes src:417's mask.  The scattered stores are spread over all CTAs.
 __global__ void __launch_bounds__(BH_THREADS)
-bh_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64_t n, double* __restrict__ padj,
-          double* __restrict__ scratch) {
-    __shared__ double wtot[32];
+bh_scan_kernel(const double* __restrict__ sp, int64_t n, double* __restrict__ scratch, double* __restrict__ tot) {
+    __shared__ double wmin[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t seg = ((n + 31) / 32 + 31) / 32 * 32;          // elements per warp, multiple of 32
-    const int64_t lo = (int64_t)wid * seg;
-    const int64_t hi = (lo + seg < n) ? lo + seg : n;             // [lo, hi)
-    const int rows = (hi > lo) ? (int)((hi - lo + 31) / 32) : 0;
-    double carry = INFINITY;
-    for (int rr = rows - 1; rr >= 0; --rr) {
-        const int64_t i = lo + (int64_t)rr * 32 + lane;
-        double v = INFINITY;
-        if (i < hi) v = sp[i] * ((double)n / (double)(i + 1));
-        for (int o = 1; o < 32; o <<= 1) {                        // inclusive suffix minimum over lanes >= lane
-            const double t = __shfl_down_sync(0xffffffffu, v, o);
-            if (lane + o < 32) v = t < v ? t : v;
-        }
-        v = carry < v ? carry : v;
-        if (i < hi) scratch[i] = v;
-        carry = __shfl_sync(0xffffffffu, v, 0);
+    const int64_t i = (int64_t)blockIdx.x * BH_THREADS + tid;
+    double v = INFINITY;
+    if (i < n) v = sp[i] * ((double)n / (double)(i + 1));
+    for (int o = 1; o < 32; o <<= 1) {                            // inclusive suffix minimum over lanes >= lane
+        const double t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v = t < v ? t : v;
     }
-    if (lane == 0) wtot[wid] = carry;   // minimum of this warp's whole segment (INFINITY if empty)
+    if (lane == 0) wmin[wid] = v;
     __syncthreads();
-    double right = INFINITY;            // minimum over the warps to the right
-    for (int w = wid + 1; w < 32; ++w) { const double t = wtot[w]; right = t < right ? t : right; }
-    for (int rr = 0; rr < rows; ++rr) {
-        const int64_t i = lo + (int64_t)rr * 32 + lane;
-        if (i < hi) {
-            double v = scratch[i];      // written by this very thread
-            v = right < v ? right : v;
-            padj[perm[i]] = v < 1.0 ? v : 1.0;
-        }
-    }
+    double right = INFINITY;                                      // warps to the right inside this CTA
+    for (int w = wid + 1; w < 32; ++w) { const double t = wmin[w]; right = t < right ? t : right; }
+    v = right < v ? right : v;
+    if (i < n) scratch[i] = v;
+    if (tid == 0) tot[blockIdx.x] = v;
 }
+
+__global__ void __launch_bounds__(BH_THREADS)
+bh_finish_kernel(const double* __restrict__ sp, const int32_t* __restrict__ perm, int64_t n,
+                 const double* __restrict__ scratch, const double* __restrict__ tot, double* __restrict__ padj,
+                 uint8_t* __restrict__ mask_new, double pval_deg, double padj_deg) {
+    __shared__ double wmin[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double right = INFINITY;                                      // minimum of the segments to the right
+    for (int b = blockIdx.x + 1 + tid; b < (int)gridDim.x; b += BH_THREADS) { const double t = tot[b]; right = t < right ? t : right; }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, right, o); right = t < right ? t : right; }
+    if (lane == 0) wmin[wid] = right;
+    __syncthreads();
+    right = wmin[lane];
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, right, o); right = t < right ? t : right; }
+    const int64_t i = (int64_t)blockIdx.x * BH_THREADS + tid;
+    if (i >= n) return;
+    double v = scratch[i];
+    v = right < v ? right : v;
+    v = v < 1.0 ? v : 1.0;
+    const int32_t g = perm[i];
+    padj[g] = v;
+    // inds = .!((pval .<= pval_deg) .&& (padj .<= padj_deg)), src:417 (sp[i] is gene g's p-value)
+    if (mask_new) mask_new[g] = !((sp[i] <= pval_deg) && (v <= padj_deg));
+}
+// ws: n + ceil(n/1024) doubles of scratch
 cudaError_t reo_launch_bh(const double* sorted_p, const int32_t* perm, int64_t n, double* padj, double* ws,
-                          cudaStream_t st) {
-    if (!ws) return cudaErrorInvalidValue;   // n doubles of scratch
-    bh_kernel<<<1, BH_THREADS, 0, st>>>(sorted_p, perm, n, padj, ws);
+                          uint8_t* mask_new, double pval_deg, double padj_deg, cudaStream_t st) {
+    if (!ws) return cudaErrorInvalidValue;
+    const unsigned nb = (unsigned)((n + BH_THREADS - 1) / BH_THREADS);
+    bh_scan_kernel<<<nb, BH_THREADS, 0, st>>>(sorted_p, n, ws, ws + n);
+    bh_finish_kernel<<<nb, BH_THREADS, 0, st>>>(sorted_p, perm, n, ws, ws + n, padj, mask_new, pval_deg, padj_deg);
     return cudaGetLastError();
 }
 

@@ -557,3 +557,36 @@ def test_randomised_shape_sweep():
     p = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "120", "11"],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_pageable_and_pinned_outputs_agree(reo, pkg):
+    """REO_OUT_PINNED (what the Python wrapper uses: direct device->host copies into page-locked outputs) and the
+    default path (pageable caller buffers, staged inside the library) return the same bytes; n_iter = 0 too."""
+    import ctypes as C
+    L = pkg._lib
+    rng = np.random.default_rng(5)
+    r, c = 700, 24
+    data = np.asfortranarray(rng.poisson(6.0, size=(r, c)).astype(np.int64))
+    gid = np.array([0] * 12 + [1] * 12, dtype=np.int32)
+    ref = (rng.random(r) < 0.3).astype(np.uint8)
+    for n_iter in (128, 0):
+        want = reo.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, n_iter, 2)
+        res = np.full((1, 15, r), -7.0)
+        ud = np.full((1, r), 9, dtype=np.int8)
+        fr = np.full((1, r), 9, dtype=np.uint8)
+        it = np.zeros(1, dtype=np.int32)
+        rc = reo._lib.reo_identify_degs(reo._h, data.ctypes.data_as(C.c_void_p), L.REO_I64, r, c, r,
+                                        gid.ctypes.data_as(C.c_void_p), 2, None, 0.01, 1.0, 0.05,
+                                        ref.ctypes.data_as(C.c_void_p), n_iter, 2, 0, res.ctypes.data_as(C.c_void_p),
+                                        ud.ctypes.data_as(C.c_void_p), fr.ctypes.data_as(C.c_void_p),
+                                        it.ctypes.data_as(C.c_void_p), None)
+        assert rc == 0
+        assert np.array_equal(res.transpose(0, 2, 1), want.result, equal_nan=True)
+        assert np.array_equal(ud, want.updown) and np.array_equal(fr, want.final_ref)
+        assert [int(it[0])] == want.iters
+    # results of earlier calls stay valid while newer ones are alive (distinct pinned blocks)
+    a = reo.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 128, 2)
+    keep = a.result.copy()
+    b = reo.identify_degs(data[::-1].copy(order="F"), gid, 2, ref, 0.01, 1.0, 0.05, 128, 2)
+    assert np.array_equal(a.result, keep, equal_nan=True) and b.result.ctypes.data != a.result.ctypes.data
