@@ -341,9 +341,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     CK(cudaMemcpyAsync(d_col_of_sample, col_of_sample.data(), c * 4, cudaMemcpyHostToDevice, D.st));
 
     CK(D.ranks.ensure((size_t)nslots * rpad * (rank_bytes / 2)));
-    if (w_hi > w_lo)
-        CK(cudaMemsetAsync((uint8_t*)D.ranks.p + (size_t)w_lo * 32 * rpad * rank_bytes, 0,
-                           (size_t)(w_hi - w_lo) * 32 * rpad * rank_bytes, D.st));
+    // no clearing: bitplanes_kernel masks pad slots and genes >= r itself
     CK(D.flags.ensure(8));
     CK(cudaMemsetAsync(D.flags.p, 0, 8 * sizeof(int), D.st));
     CK(D.fblist.ensure(std::max<int64_t>(nmy, 1)));
@@ -426,14 +424,16 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
             h->kernel_launches++;
         }
     }
+    const bool more_ranked = (D.h_counts[3] > 0 || nfb > 0) && !D.h_counts[0];   // a later tier ran after the read-back
     if (shard) {   // non-integrality and the largest dense rank are properties of the whole matrix
         const ncclResult_t nr = g_nccl.AllReduce(D.flags.p, D.flags.p + 4, 4, ncclInt32, ncclMax, D.comm, D.st);
         if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(nr));
         CK(cudaMemcpyAsync(D.h_counts, D.flags.p + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
-    } else {
+        CK(cudaStreamSynchronize(D.st));
+    } else if (more_ranked) {
         CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
     }
-    CK(cudaStreamSynchronize(D.st));
     if (D.h_counts[0]) {
         // non-integral values: the 0.1 tie band of is_greater (src:72) is not transitive, so ranks cannot be
         // used -- stage the raw values as FP64 and let the pair kernel compare them directly
@@ -543,15 +543,17 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     return REO_OK;
 }
 
-// full build for the mask in mask_dev
-int build_tables_full(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* mask_dev) {
+// full build for the mask in mask_dev; ncols = its population count when the host already knows it (-1: read it back)
+int build_tables_full(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* mask_dev, int ncols = -1) {
     const ReoStaged& S = D.S;
     CKL(reo_launch_mask_to_list(mask_dev, S.r, D.col_gene.p, D.counts.p + 4, D.st));
     h->kernel_launches++;
-    CK(cudaMemcpyAsync(D.h_counts + 4, D.counts.p + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
     CK(cudaMemsetAsync(D.table.p, 0, (size_t)D.table_rows * 9 * sizeof(int32_t), D.st));
-    CK(cudaStreamSynchronize(D.st));
-    const int ncols = D.h_counts[4];
+    if (ncols < 0) {
+        CK(cudaMemcpyAsync(D.h_counts + 4, D.counts.p + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
+        ncols = D.h_counts[4];
+    }
     const bool all = (ncols == (int)S.r);
     return launch_tables(h, D, P, all ? D.iota.p : D.col_gene.p, nullptr, ncols, all);
 }
@@ -1164,8 +1166,10 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         int i_iter = 0, n_eval = 0, converged = 0;
         bool have_tables = false;
         while (i_iter < n_iter) {
-            if (!have_tables) {
-                if ((rc = build_tables_full(h, D, P, mask_cur))) return rc;
+            if (!have_tables) {   // the initial mask is a host array: count it here, no read-back
+                int n0 = 0;
+                for (int64_t i = 0; i < r; ++i) n0 += ref_mask[i] != 0;
+                if ((rc = build_tables_full(h, D, P, mask_cur, n0))) return rc;
                 have_tables = true;
             }
             if ((rc = allgather_tables(h, D))) return rc;
@@ -1195,7 +1199,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
                     std::swap(mask_cur, mask_new);
                 } else {
                     std::swap(mask_cur, mask_new);
-                    if ((rc = build_tables_full(h, D, P, mask_cur))) return rc;
+                    if ((rc = build_tables_full(h, D, P, mask_cur, n_inds))) return rc;
                 }
             }
         }

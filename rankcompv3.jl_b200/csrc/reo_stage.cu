@@ -15,10 +15,10 @@
 
 #include "reo_internal.cuh"
 
-#define RK_THREADS 1024                 // wide tier / fallback: one CTA per SM
-#define BM_WORDS 40960                  // wide tier: bitmap words in shared memory (1,310,720 distinct values)
-#define RK_THREADS_S 256                // small tier: value range < 65536 (counts of most samples): 8 CTAs per SM
-#define BM_WORDS_S 2048
+#define RK_THREADS 1024                 // both tiers and the fallback
+#define BM_WORDS 40960                  // wide tier: bitmap words in shared memory (1,310,720 distinct values), 1 CTA per SM
+#define BM_WORDS_S 2048                 // small tier: value range < 65536 (counts of most samples), 2 CTAs per SM
+#define RK_STASH_MAX_R 51200            // small tier keeps (v - min) as u16 in shared memory up to this many genes
 #define BM_GROUP 8                      // words per prefix entry
 
 template <typename T>
@@ -73,8 +73,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int* red, int* total) {
 
 // One CTA per sample column.  NTHR threads, BMW bitmap words: columns whose value range does not fit the bitmap are
 // appended to over_list (their list positions) for the next tier.  `cols` (optional) lists the positions to process.
-template <typename T, typename RT, int NTHR, int BMW>
-__global__ void __launch_bounds__(NTHR, (NTHR == RK_THREADS) ? 1 : 8)
+// The column is read from DRAM once: with 2 x 148 resident CTAs the columns in flight (2 x 148 x 8r bytes, 71 MB at
+// 30k genes) stay in L2 for the second pass, and STASH keeps (v - min) as u16 in shared memory for the third.
+template <typename T, typename RT, int NTHR, int BMW, bool STASH>
+__global__ void __launch_bounds__(NTHR, (BMW == BM_WORDS) ? 1 : 2)
 rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t col0, const int32_t* __restrict__ cols,
                     const int32_t* __restrict__ src_col, const int32_t* __restrict__ sample_id,
                     const int32_t* __restrict__ slot_of_sample, RT* __restrict__ ranks, int64_t rpad,
@@ -87,6 +89,7 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     uint32_t* pre = sm + BMW;            // [BMP]
     int* red = (int*)(pre + BMP);        // [40]
     long long* redl = (long long*)(red + 40);  // [64]
+    uint16_t* stash = (uint16_t*)(redl + 64);  // [r] when STASH
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t j = cols ? (int64_t)cols[blockIdx.x] : col0 + blockIdx.x;   // position in this rank's column list
@@ -131,7 +134,10 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     for (int64_t g = tid; g < r; g += RK_THREADS_L) {
         long long v; to_ll<T>(col[g], v);
         const uint32_t k = (uint32_t)((unsigned long long)v - (unsigned long long)mn);
-        atomicOr(&bm[k >> 5], 1u << (k & 31));
+        if (STASH) stash[g] = (uint16_t)k;
+        const uint32_t bit = 1u << (k & 31);
+        // sparse counts put most genes on the same few values: test first, the atomic is the rare case
+        if (!(((volatile uint32_t*)bm)[k >> 5] & bit)) atomicOr(&bm[k >> 5], bit);
     }
     __syncthreads();
     // phase 3: exclusive prefix of popcounts per group of BM_GROUP words
@@ -160,8 +166,9 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     const int64_t slot = slot_of_sample[s];
     RT* __restrict__ out = ranks + slot * rpad;
     for (int64_t g = tid; g < r; g += RK_THREADS_L) {
-        long long v; to_ll<T>(col[g], v);
-        const uint32_t k = (uint32_t)((unsigned long long)v - (unsigned long long)mn);
+        uint32_t k;
+        if (STASH) k = stash[g];
+        else { long long v; to_ll<T>(col[g], v); k = (uint32_t)((unsigned long long)v - (unsigned long long)mn); }
         const uint32_t wq = k >> 5;
         uint32_t rk = pre[wq / BM_GROUP];
         for (uint32_t w = (wq / BM_GROUP) * BM_GROUP; w < wq; ++w) rk += __popc(bm[w]);
@@ -229,7 +236,7 @@ rank_fallback_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const in
 
 static size_t rank_smem_bytes(int bmw) { return (size_t)(bmw + bmw / BM_GROUP + 40) * 4 + 64 * 8 + 16; }
 
-// tier 0 (small bitmap, 8 CTAs/SM) over list positions [col0, col0+ncols): overflow -> wide_list / flags[3]
+// tier 0 (small bitmap, 2 CTAs/SM) over list positions [col0, col0+ncols): overflow -> wide_list / flags[3]
 // tier 1 (wide bitmap, 1 CTA/SM) over wide_list: overflow -> fallback_list / flags[1]
 template <typename T, typename RT>
 static cudaError_t launch_rank_t(const void* data, int64_t r, int64_t ld, int64_t col0, int ncols, const int32_t* cols,
@@ -240,14 +247,21 @@ static cudaError_t launch_rank_t(const void* data, int64_t r, int64_t ld, int64_
     cudaError_t e;
     if (wide) {
         const size_t smem = rank_smem_bytes(BM_WORDS);
-        e = cudaFuncSetAttribute(rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS><<<ncols, RK_THREADS, smem, st>>>(
+        rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS, false><<<ncols, RK_THREADS, smem, st>>>(
+            (const T*)data, r, ld, col0, cols, src_col, sample_id, slot_of_sample, (RT*)ranks, rpad, max_distinct, flags,
+            over_count, over_list);
+    } else if (r <= RK_STASH_MAX_R) {
+        const size_t smem = rank_smem_bytes(BM_WORDS_S) + (size_t)r * 2 + 16;
+        e = cudaFuncSetAttribute(rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS_S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS_S, true><<<ncols, RK_THREADS, smem, st>>>(
             (const T*)data, r, ld, col0, cols, src_col, sample_id, slot_of_sample, (RT*)ranks, rpad, max_distinct, flags,
             over_count, over_list);
     } else {
         const size_t smem = rank_smem_bytes(BM_WORDS_S);
-        rank_columns_kernel<T, RT, RK_THREADS_S, BM_WORDS_S><<<ncols, RK_THREADS_S, smem, st>>>(
+        rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS_S, false><<<ncols, RK_THREADS, smem, st>>>(
             (const T*)data, r, ld, col0, cols, src_col, sample_id, slot_of_sample, (RT*)ranks, rpad, max_distinct, flags,
             over_count, over_list);
     }
@@ -296,49 +310,87 @@ cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int
 }
 
 // ---- bit-plane transpose ------------------------------------------------------------------------
-// block (64, 4): thread (l, y) builds the NP words of gene t*64+l for sample word w = 4*blockIdx.y+y.
-template <typename RT>
+// CTA = gene tile t x 4 sample words (128 slots), 256 threads.  The 128 x 64 ranks are loaded with genes along the
+// lanes (coalesced), parked in shared memory and read back with SAMPLES along the lanes, so one __ballot_sync per
+// plane turns 32 samples of one gene into the finished word; lane j keeps the words of gene j and the stores are
+// coalesced again.  Cost per (gene, sample): the coin hash (~9 integer ops) + (NPB x 3 + 2) / 32 instructions.
+// NPB = compile-time bound on the plane count (NP <= NPB): the plane loop must unroll over exactly the planes in use.
+template <typename RT, int NPB>
 __global__ void __launch_bounds__(256)
 bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
                  const int32_t* __restrict__ sample_of_slot, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo,
                  uint32_t seed_hi, uint32_t* __restrict__ planes) {
     // words [w_lo, w_lo + w_n) of the staged order are written at local index (w - w_lo) with w_stride words per tile
-    const int t = blockIdx.x, l = threadIdx.x;
-    const int wl = blockIdx.y * 4 + threadIdx.y;
-    if (wl >= w_n) return;
-    const int w = w_lo + wl;
-    const int64_t g = (int64_t)t * REO_TILE + l;
-    uint32_t wd[REO_MAX_PLANES];
-#pragma unroll
-    for (int p = 0; p < REO_MAX_PLANES; ++p) wd[p] = 0u;
-    if (g < r) {
-#pragma unroll 4
-        for (int b = 0; b < 32; ++b) {
-            const int64_t S = (int64_t)w * 32 + b;
-            const int so = sample_of_slot[S];
-            if (so >= 0) {
-                const uint32_t rk = ranks[S * rpad + g];
-                wd[0] |= reo_coin_u(seed_lo, seed_hi, (uint32_t)g, (uint32_t)so) << b;
-#pragma unroll
-                for (int q = 0; q < REO_MAX_BITS; ++q) wd[q + 1] |= ((rk >> q) & 1u) << b;
+    constexpr int PER = 4 / sizeof(RT);                 // ranks per 32-bit word
+    constexpr int LD = REO_TILE / PER + 1;              // row stride in words, odd: conflict-free column reads
+    __shared__ uint32_t tile[128 * LD];                 // [slot][gene]
+    __shared__ uint32_t ghash[REO_TILE];                // inner hash of the coin, per gene
+    __shared__ int so_s[128];
+    const int t = blockIdx.x, wl0 = blockIdx.y * 4;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < REO_TILE) ghash[tid] = reo_mix32(seed_lo ^ ((uint32_t)(t * REO_TILE + tid) * 0x9E3779B1u));
+    if (tid < 128) {
+        const int wl = wl0 + (tid >> 5);
+        so_s[tid] = wl < w_n ? sample_of_slot[(int64_t)(w_lo + wl) * 32 + (tid & 31)] : -1;
+    }
+    __syncthreads();
+    const int64_t gbase = (int64_t)t * REO_TILE;
+    for (int idx = tid; idx < 128 * (REO_TILE / PER); idx += 256) {
+        const int row = idx / (REO_TILE / PER), cw = idx % (REO_TILE / PER);
+        uint32_t v = 0u;
+        if (so_s[row] >= 0) {
+            const int64_t S = (int64_t)(w_lo + wl0 + (row >> 5)) * 32 + (row & 31);
+            const int64_t g0 = gbase + (int64_t)cw * PER;
+            if (g0 < r) {
+                v = *reinterpret_cast<const uint32_t*>(ranks + S * rpad + g0);   // rpad is a multiple of 64: aligned
+                if (PER == 2 && g0 + 1 >= r) v &= 0xffffu;                       // genes >= r are not ranked
             }
         }
+        tile[row * LD + cw] = v;
     }
-    uint32_t* out = planes + ((size_t)t * w_stride + wl) * NP * REO_TILE + l;
+    __syncthreads();
+    const int q = wid >> 1, hf = wid & 1;               // this warp: sample word q of the CTA, genes hf*32 .. hf*32+31
+    const int wl = wl0 + q;
+    if (wl >= w_n) return;
+    const int row = q * 32 + lane;
+    const int so = so_s[row];
+    const uint32_t sterm = (uint32_t)so * 0x85EBCA77u + seed_hi;
+    uint32_t mine[NPB];
 #pragma unroll
-    for (int p = 0; p < REO_MAX_PLANES; ++p)
-        if (p < NP) out[(size_t)p * REO_TILE] = wd[p];
+    for (int p = 0; p < NPB; ++p) mine[p] = 0u;
+#pragma unroll 2
+    for (int j = 0; j < 32; ++j) {
+        const int gi = hf * 32 + j;
+        uint32_t rk = tile[row * LD + gi / PER];
+        if (PER == 2) rk = (gi & 1) ? (rk >> 16) : (rk & 0xffffu);
+        const bool live = so >= 0 && gbase + gi < r;
+        const uint32_t coin = live ? (reo_mix32(ghash[gi] + sterm) >> 31) : 0u;
+        const uint32_t w0 = __ballot_sync(0xffffffffu, coin);
+        if (lane == j) mine[0] = w0;
+#pragma unroll
+        for (int p = 1; p < NPB; ++p) {                  // planes >= NP come out zero (rk < 2^(NP-1)) and are not stored
+            const uint32_t wv = __ballot_sync(0xffffffffu, (rk & (1u << (p - 1))) != 0u);
+            if (lane == j) mine[p] = wv;
+        }
+    }
+    uint32_t* out = planes + ((size_t)t * w_stride + wl) * NP * REO_TILE + hf * 32 + lane;
+#pragma unroll
+    for (int p = 0; p < NPB; ++p)
+        if (p < NP) out[(size_t)p * REO_TILE] = mine[p];
 }
 
 cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
                                  int NT, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo, uint32_t seed_hi,
                                  uint32_t* planes, cudaStream_t st) {
     if (w_n <= 0) return cudaSuccess;
-    dim3 grid(NT, (w_n + 3) / 4), block(REO_TILE, 4);
-    if (rank_bytes == 2)
-        bitplanes_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, seed_lo, seed_hi, planes);
-    else
-        bitplanes_kernel<uint32_t><<<grid, block, 0, st>>>((const uint32_t*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, seed_lo, seed_hi, planes);
+    dim3 grid(NT, (w_n + 3) / 4), block(256);
+#define LAUNCH_BP(RT, NPB) bitplanes_kernel<RT, NPB><<<grid, block, 0, st>>>((const RT*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, seed_lo, seed_hi, planes)
+#define LAUNCH_BPN(RT)                                                                                                 \
+    if (NP <= 5) LAUNCH_BP(RT, 5); else if (NP <= 9) LAUNCH_BP(RT, 9); else if (NP <= 13) LAUNCH_BP(RT, 13);           \
+    else if (NP <= 17) LAUNCH_BP(RT, 17); else LAUNCH_BP(RT, REO_MAX_PLANES)
+    if (rank_bytes == 2) { LAUNCH_BPN(uint16_t); } else { LAUNCH_BPN(uint32_t); }
+#undef LAUNCH_BPN
+#undef LAUNCH_BP
     return cudaGetLastError();
 }
 
