@@ -13,6 +13,7 @@ Everything numeric is computed by libreo_cuda.so on the GPU; there is no CPU fal
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from dataclasses import dataclass, field
 
@@ -45,17 +46,21 @@ _pinned_pool: dict = {}
 _PINNED_ROUND = 1 << 16
 
 
-def _pinned_empty(shape, dtype):
-    """np.empty(shape, dtype) in page-locked memory (size rounded up to 64 KiB so blocks recycle across calls)."""
-    dt = np.dtype(dtype)
-    n = int(np.prod(shape)) * dt.itemsize
+def _pinned_bytes(n):
+    """n bytes (uint8 array) of page-locked memory; sizes are rounded up to 64 KiB so blocks recycle across calls."""
     nbytes = max((n + _PINNED_ROUND - 1) // _PINNED_ROUND, 1) * _PINNED_ROUND
     free = _pinned_pool.get(nbytes)
     ptr = free.pop() if free else L.load().reo_host_alloc(nbytes)
     if not ptr:
         raise MemoryError(f"reo_host_alloc({nbytes}) failed")
-    block = _PinnedBlock(ptr, nbytes)
-    return np.asarray(block)[:n].view(dt).reshape(shape)
+    return np.asarray(_PinnedBlock(ptr, nbytes))
+
+
+def _pinned_empty(shape, dtype):
+    """np.empty(shape, dtype) in page-locked memory."""
+    dt = np.dtype(dtype)
+    n = math.prod(shape) * dt.itemsize
+    return _pinned_bytes(n)[:n].view(dt).reshape(shape)
 
 
 class ReoError(RuntimeError):
@@ -79,7 +84,7 @@ def _raise(code: int, msg: str):
 
 
 def _ptr(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    return None if a is None else a.ctypes.data   # plain address: c_void_p argtypes take ints
 
 
 _DT = {np.dtype(np.int64): L.REO_I64, np.dtype(np.float64): L.REO_F64,
@@ -204,15 +209,21 @@ class Reo:
         gid = np.ascontiguousarray(group_id, dtype=np.int32)
         if len(gid) != c:
             raise ValueError("DimensionMismatch: 'data' and 'group' do not have compatiable sizes")  # src:355
-        ref = np.ascontiguousarray(np.asarray(ref_mask) != 0, dtype=np.uint8)
+        ref = np.asarray(ref_mask)
+        if ref.dtype == np.bool_ and ref.flags.c_contiguous:
+            ref = ref.view(np.uint8)             # a BitVector-like mask: its bytes are already 0/1
+        else:
+            ref = np.ascontiguousarray(ref != 0, dtype=np.uint8)
         if len(ref) != r:
             raise ValueError("DimensionMismatch: 'ref_gene' and 'data' do not have compatiable sizes")
         K = 1 if gnum == 2 else max(int(gnum), 1)
         thr = None if thresholds is None else np.asfortranarray(np.asarray(thresholds, dtype=np.int32))
-        # outputs live in recycled page-locked blocks: the library copies device->host straight into them
-        result = _pinned_empty((K, 15, r), np.float64)   # column-major r x 15 per k, filled by the library
-        updown = _pinned_empty((K, r), np.int8)
-        final_ref = _pinned_empty((K, r), np.uint8)
+        # outputs live in ONE recycled page-locked block: the library copies device->host straight into it
+        nres = K * 15 * r * 8
+        blk = _pinned_bytes(nres + 2 * K * r)
+        result = blk[:nres].view(np.float64).reshape(K, 15, r)   # column-major r x 15 per k, filled by the library
+        updown = blk[nres:nres + K * r].view(np.int8).reshape(K, r)
+        final_ref = blk[nres + K * r:nres + 2 * K * r].reshape(K, r)
         flags |= L.REO_OUT_PINNED
         iters = np.zeros(K, dtype=np.int32)
         st = L.ReoStats()
