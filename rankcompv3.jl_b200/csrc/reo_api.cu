@@ -520,9 +520,13 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     p.ntc = ntc;
     const int ntr = p.t1 - p.t0;
     if (ntr <= 0) return REO_OK;
-    const int want_items = 16 * 3 * D.num_sms;   // ~16 work items per resident CTA: small tail
+    // Work items = row tile x chunk of column tiles, handed out dynamically.  At least ~16 items per resident CTA;
+    // beyond that an item only needs enough sample words (~64) to amortise its prologue and table flush -- with
+    // thousands of samples one column tile per item keeps the tail of the launch below 1 %.
+    const int want_items = 16 * 3 * D.num_sms;
     int njc = std::max(1, std::min(ntc, (want_items + ntr - 1) / ntr));
     p.jchunk = (ntc + njc - 1) / njc;
+    p.jchunk = std::min(p.jchunk, std::max(1, (64 + S.W - 1) / S.W));
     p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;
     p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
     p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;
