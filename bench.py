@@ -230,6 +230,7 @@ def main():
         for _ in range(warmup):
             one(mat)
         total_ms, stats = 0.0, []
+        by_rank = [0.0] * world
         for _ in range(steps):
             flush.fill_(1)                      # L2 flush between timed iterations (inputs are 32 MB < L2)
             barrier()
@@ -241,15 +242,26 @@ def main():
             torch.cuda.synchronize()
             ms = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
             if dist is not None:
+                every = [torch.zeros_like(ms) for _ in range(world)]
+                dist.all_gather(every, ms)
+                for i, t in enumerate(every):
+                    by_rank[i] += float(t.item()) / steps
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            else:
+                by_rank[0] += float(ms.item()) / steps
             total_ms += float(ms.item())
             stats.append(out.stats)
+        timed.by_rank = by_rank
         return total_ms, stats, out
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, st_dev, out_dev = timed(dmat, args.steps, args.warmup)
+    ms_by_rank = [round(x, 4) for x in timed.by_rank]
+    if os.environ.get("REO_BENCH_RANKLOG"):      # diagnosis: every rank's own view of its last timed step
+        with open(os.path.join(os.environ["REO_BENCH_RANKLOG"], f"rank_{rank}.json"), "w") as f:
+            json.dump({"rank": rank, "ms_by_rank": ms_by_rank, "last_step": st_dev[-1]}, f)
     ms_e2e, st_e2e, out_e2e = timed(hmat, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -359,6 +371,7 @@ def main():
             "stage_ms": {"staging": st_dev[-1]["ms_stage"], "pairs": st_dev[-1]["ms_pairs"],
                          "stats": st_dev[-1]["ms_stats"], "total_device": st_dev[-1]["ms_total"],
                          "call_wall": st_dev[-1]["ms_wall"]},
+            "ms_per_step_by_rank": ms_by_rank,   # `ms_per_step` is the per-step MAX over ranks
             "clocks": clocks, "roofline": roof, "roofline_staging": roof_k1,
         }
         if probe is not None:

@@ -314,8 +314,9 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
 
     // K1 sharding (NCCL communicator present): this rank copies, ranks and bit-slices only the sample words
     // [w_lo, w_hi); the staged blocks are all-gathered over NVLink and re-ordered into planes[t][w].
-    // (small matrices are staged redundantly: two extra collectives cost more than ranking 200 columns)
-    int64_t shard_min = (int64_t)1 << 24;
+    // (small device-resident matrices are staged redundantly: two extra collectives cost more than ranking 200
+    // columns; for host input the share of the host->device copy saved pays much earlier)
+    int64_t shard_min = (flags & REO_DATA_ON_DEVICE) ? (int64_t)1 << 24 : (int64_t)1 << 20;
     if (const char* e = getenv("REO_K1_SHARD_MIN")) shard_min = atoll(e);   // tests force the sharded path on small inputs
     const bool shard = (h->world > 1 && D.comm != nullptr && r * c >= shard_min);
     const int wq = shard ? (W + h->world - 1) / h->world : W;

@@ -344,6 +344,13 @@ def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
                 fref = np.arange(300) % 4 == 0
                 fwant = coracle.identify_degs(fdata, fgid, 3, fthr, 1.0, 0.05, fref, 128, 5, seed=7)
                 check_full(h.identify_degs(fdata, fgid, 3, fref, 0.01, 1.0, 0.05, 128, 5), fwant)
+                # fewer sample words than devices: 10 + 12 samples share ONE word, every other device stages nothing
+                sdata, sgroup = small_case(77, 300, 10, 12)
+                slev, sgid = oracle.group_levels(sgroup)
+                sthr = coracle.thresholds_for(sgid, 2, 0.01)
+                sref = np.arange(300) % 3 == 0
+                swant = coracle.identify_degs(sdata, sgid, 2, sthr, 1.0, 0.05, sref, 128, 5, seed=7)
+                check_full(h.identify_degs(sdata, sgid, 2, sref, 0.01, 1.0, 0.05, 128, 5), swant)
         finally:
             os.environ.pop("REO_K1_SHARD_MIN", None)
 
