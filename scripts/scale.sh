@@ -5,9 +5,9 @@ OUT=gpurun_out/scale_$N.jsonl
 : > $OUT
 for wl in c2_bulk_20kx200 c5_allref_30kx20k; do
   if [ "$N" = "1" ]; then
-    timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --workload $wl >> $OUT 2> gpurun_out/scale_$N.err
+    timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --workload $wl >> $OUT 2> gpurun_out/scale_$N.err
   else
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline --workload $wl >> $OUT 2> gpurun_out/scale_$N.err
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --workload $wl >> $OUT 2> gpurun_out/scale_$N.err
   fi
   echo "rc=$? $wl"
 done
