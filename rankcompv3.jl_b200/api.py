@@ -36,21 +36,33 @@ class _PinnedBlock:
         self.__array_interface__ = {"data": (ptr, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
 
     def __del__(self):
+        global _pinned_pooled
         try:
-            _pinned_pool.setdefault(self.nbytes, []).append(self.ptr)
+            if _pinned_pooled + self.nbytes <= _PINNED_POOL_CAP:
+                _pinned_pool.setdefault(self.nbytes, []).append(self.ptr)
+                _pinned_pooled += self.nbytes
+            else:
+                L.load().reo_host_free(self.ptr)
         except Exception:  # interpreter shutdown
             pass
 
 
 _pinned_pool: dict = {}
+_pinned_pooled = 0                 # bytes parked in the pool
+_PINNED_POOL_CAP = 1 << 28         # beyond 256 MiB idle blocks go back to the driver
 _PINNED_ROUND = 1 << 16
 
 
 def _pinned_bytes(n):
     """n bytes (uint8 array) of page-locked memory; sizes are rounded up to 64 KiB so blocks recycle across calls."""
     nbytes = max((n + _PINNED_ROUND - 1) // _PINNED_ROUND, 1) * _PINNED_ROUND
+    global _pinned_pooled
     free = _pinned_pool.get(nbytes)
-    ptr = free.pop() if free else L.load().reo_host_alloc(nbytes)
+    if free:
+        ptr = free.pop()
+        _pinned_pooled -= nbytes
+    else:
+        ptr = L.load().reo_host_alloc(nbytes)
     if not ptr:
         raise MemoryError(f"reo_host_alloc({nbytes}) failed")
     return np.asarray(_PinnedBlock(ptr, nbytes))

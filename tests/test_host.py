@@ -81,3 +81,39 @@ def test_shard_plan(pkg):
         assert tpr == -(-nt // world) and len(ranges) == world
         covered = [t for (a, b) in ranges for t in range(a, b)]
         assert covered == list(range(nt))
+
+
+def test_pinned_output_pool_recycles_and_caps(pkg, monkeypatch):
+    """The Python wrapper's page-locked output blocks are recycled by size and handed back to the driver beyond the
+    pool cap (allocator stubbed: no GPU needed)."""
+    api = pkg.api
+
+    class Stub:
+        def __init__(self):
+            self.allocs, self.freed, self.keep = 0, [], []
+
+        def reo_host_alloc(self, nbytes):
+            self.allocs += 1
+            b = (ctypes.c_char * nbytes)()
+            self.keep.append(b)
+            return ctypes.addressof(b)
+
+        def reo_host_free(self, p):
+            self.freed.append(p)
+
+    st = Stub()
+    monkeypatch.setattr(api.L, "load", lambda: st)
+    monkeypatch.setattr(api, "_pinned_pool", {})
+    monkeypatch.setattr(api, "_pinned_pooled", 0)
+    a = api._pinned_empty((3, 5), np.float64)
+    a[:] = 1.5
+    p0 = a.ctypes.data
+    v = a.T                      # views keep the block alive
+    del a
+    assert v[0, 0] == 1.5 and st.allocs == 1 and not api._pinned_pool
+    del v
+    b = api._pinned_empty((15,), np.float64)
+    assert b.ctypes.data == p0 and st.allocs == 1     # recycled, not re-allocated
+    monkeypatch.setattr(api, "_PINNED_POOL_CAP", 0)
+    del b
+    assert st.freed == [p0] and api._pinned_pooled == 0
