@@ -579,8 +579,7 @@ int allgather_tables(reo_handle_t h, ReoDev& D) {
     return REO_OK;
 }
 
-// One evaluation of src:402-417 on the current tables: McCullagh per gene, sort + trimmed std, empirical-null p,
-// BH, new mask, symmetric difference, and the three counters the host decides on (read back into pinned memory).
+// One evaluation of src:402-417 on the current tables = enqueue_mcc + enqueue_eval.
 // src:402-406: tables -> result columns 2..14.  Those 13 columns are final for this evaluation, so their
 // device->host copy starts on the copy stream at once and overlaps the rest of the sequence (early_dst: the host
 // image of `result` for this level, pinned).
@@ -597,6 +596,8 @@ int enqueue_mcc(reo_handle_t h, ReoDev& D, int64_t r, double* early_dst) {
     return REO_OK;
 }
 
+// src:409-417: sort + trimmed std, empirical-null p, BH, new mask, symmetric difference, and the three counters the
+// host decides on (read back into pinned memory).
 int enqueue_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double padj_deg, uint8_t* mask_cur,
                  uint8_t* mask_new) {
     CKL(reo_launch_sort_f64(D.result.p + (size_t)r * 11, r, D.sorted.p, D.perm.p, D.sortws, D.st));     // src:409
