@@ -142,6 +142,7 @@ def run_reference(args, pkg):
     if rank != 0:
         return
     _, co = ge.load_oracle()
+    co.use_all_cores()                      # torchrun exports OMP_NUM_THREADS=1
     data, gid, ref = make_workload(pkg, args.workload)
     thr = co.thresholds_for(gid, 2, 0.01)
     cols = np.nonzero(ref)[0]
@@ -378,6 +379,7 @@ def main():
             line["scaling_probe"] = probe
         if not args.no_cpu_baseline:
             _, co = ge.load_oracle()
+            co.use_all_cores()
             line["cpu_baseline"], _ = cpu_baseline(pkg, co, data, gid, ref)
         print(json.dumps(line))
     h.close()

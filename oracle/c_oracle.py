@@ -30,6 +30,8 @@ def lib():
         L.reo_oracle_u.restype = C.c_uint32
         L.reo_oracle_u.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
         L.reo_oracle_num_threads.restype = C.c_int
+        L.reo_oracle_set_threads.restype = None
+        L.reo_oracle_set_threads.argtypes = [C.c_int]
         L.reo_oracle_threshold.restype = C.c_int
         L.reo_oracle_threshold.argtypes = [C.c_int, C.c_double]
         L.reo_oracle_mccullagh.restype = None
@@ -69,6 +71,16 @@ def _colmajor_f64(data):
 
 def num_threads() -> int:
     return int(lib().reo_oracle_num_threads())
+
+
+def use_all_cores() -> int:
+    """OpenMP threads = the cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().reo_oracle_set_threads(int(n))
+    return num_threads()
 
 
 def threshold(n: int, pval: float) -> int:

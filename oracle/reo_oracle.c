@@ -43,6 +43,15 @@ uint32_t reo_oracle_u(uint64_t seed, uint32_t i, uint32_t s) {
     return h >> 31;
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timing harness asks for all host cores explicitly */
+void reo_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int reo_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
