@@ -13,6 +13,18 @@ def shard_plan(n_tiles: int, world: int):
     return tpr, [(min(n_tiles, q * tpr), min(n_tiles, (q + 1) * tpr)) for q in range(world)]
 
 
+def word_shard_plan(n_words: int, world: int):
+    """K1 sharding: (words_per_rank, [(w_lo, w_hi) per rank]) over the staged sample words -- mirrors do_stage() in
+    csrc/reo_api.cu.  Ranks past the last word stage nothing; the all-gathered blocks are padded to words_per_rank."""
+    wq = -(-n_words // world)
+    return wq, [(min(n_words, q * wq), min(n_words, (q + 1) * wq)) for q in range(world)]
+
+
+def k1_is_sharded(r: int, c: int, world: int, data_on_device: bool) -> bool:
+    """Staging is sharded from 2^24 values resident in HBM, from 2^20 values for host input (mirrors do_stage())."""
+    return world > 1 and r * c >= (1 << 24 if data_on_device else 1 << 20)
+
+
 def table_slice_bytes(n_tiles: int, world: int) -> int:
     tpr, _ = shard_plan(n_tiles, world)
     return tpr * TILE * 9 * 4
