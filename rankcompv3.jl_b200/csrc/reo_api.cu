@@ -528,6 +528,8 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     int njc = std::max(1, std::min(ntc, (want_items + ntr - 1) / ntr));
     p.jchunk = (ntc + njc - 1) / njc;
     p.jchunk = std::min(p.jchunk, std::max(1, (64 + S.W - 1) / S.W));
+    const int cts = reo_pairs_col_tiles_per_step(S.flt);   // whole steps: no half-empty step at the end of a chunk
+    p.jchunk = (p.jchunk + cts - 1) / cts * cts;
     p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;
     p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
     p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;

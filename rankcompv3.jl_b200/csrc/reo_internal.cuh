@@ -81,6 +81,7 @@ struct ReoPairParams {
 struct ReoDev;  // per-device state (reo_api.cu)
 
 cudaError_t reo_launch_pairs(const ReoPairParams& p, int num_sms, cudaStream_t st);
+int reo_pairs_col_tiles_per_step(bool flt);   // 1, or 2 when the pair kernel is built with the 4x8 register tile
 cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word_order, int WA, const int32_t* rows,
                                          int nrows, const int32_t* cols, int ncols, int32_t* nre, int32_t* rest,
                                          int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB,

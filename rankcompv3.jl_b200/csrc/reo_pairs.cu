@@ -48,14 +48,29 @@
 #define PK_SMEM_BUDGET (70 * 1024)
 #endif
 #define PK_LUT_MAX_WORDS 4096   // lookup-table words (16 KB) above which the compare path is used
+// Columns per thread: 4 (CTA tile 64 x 64, 4x4 pairs per thread) or 8 (CTA tile 64 x 128: two column tiles per step,
+// 4x8 pairs per thread -- 12 operand words per 32 LOP3 instead of 8 per 16, at 2 CTAs per SM).
+#ifndef PK_NB
+#define PK_NB 4
+#endif
+#if PK_NB == 8
+#define PK_CTAS_NB 2
+#ifndef PK_SMEM_BUDGET_NB
+#define PK_SMEM_BUDGET_NB (104 * 1024)
+#endif
+#else
+#define PK_CTAS_NB PK_CTAS_PER_SM
+#define PK_SMEM_BUDGET_NB PK_SMEM_BUDGET
+#endif
 
 #define PKF_FIRST_J 1
 #define PKF_LAST_J 2
 #define PKF_LAST_ITEM 4
 #define PKF_TERM 8
+#define PKF_SECOND 16     // the step carries a second column tile (J + 1)
 
 struct PkMeta { int ti, J, w0, nw, flags, pad0, pad1, pad2; };
-struct PkProd { int count, step, nsteps, ti, J, ch, done, pad1; };   // producer state (shared memory)
+struct PkProd { int count, step, nsteps, ti, J, ch, done, jend; };   // producer state (shared memory)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -123,14 +138,15 @@ __device__ __forceinline__ uint32_t reo_class(int cnt, int n, int thr) {
 //      transitive, so ranks cannot be used; an operand word is [64 coin words][32 samples][64 genes] FP64
 //      and the 32 "is greater" bits of a word come from FP64 compares on the raw values instead of the
 //      LOP3 chain.  Everything around it (ring, classification, tables) is shared with the rank path.
-template <int NPT, bool LUT, bool FLT>
-__global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair_kernel(const ReoPairParams p) {
+template <int NPT, bool LUT, bool FLT, int NB>
+__global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : (NB == 8 ? 2 : PK_CTAS_PER_SM)) reo_pair_kernel(const ReoPairParams p) {
+    constexpr int NCT = NB / 4;                          // column tiles per step
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int NP = NPT > 0 ? NPT : p.NP;
     const int KW = p.KW;
     const int op_words = FLT ? REO_FLT_OPWORDS : NP * REO_TILE;   // words of one operand tile for one sample word
     const uint32_t op_bytes = (uint32_t)op_words * 4u;
-    const int stage_words = 2 * KW * op_words;          // rows then columns
+    const int stage_words = (1 + NCT) * KW * op_words;  // rows then columns (then the second column tile)
     uint32_t* stages = reinterpret_cast<uint32_t*>(smem_raw);
     int32_t* tab_s = reinterpret_cast<int32_t*>(stages + (size_t)PK_NS * stage_words);      // [9][64]
     PkMeta* metas = reinterpret_cast<PkMeta*>(tab_s + REO_TILE * 9);                         // 32-byte entries
@@ -213,20 +229,21 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
             const int jbeg = (item - it_row * p.njchunks) * p.jchunk;
             const int jend = min(jbeg + p.jchunk, p.ntc);
             pst->ti = p.t0 + it_row;
-            pst->J = jbeg; pst->ch = 0;
-            pst->nsteps = (jend - jbeg) * nchunks;
+            pst->J = jbeg; pst->ch = 0; pst->jend = jend;
+            pst->nsteps = ((jend - jbeg + NCT - 1) / NCT) * nchunks;
             pst->step = 0;
         }
         const int st = pst->step, ti = pst->ti;
         const int J = pst->J, ch = pst->ch;      // (column tile, word chunk) advance without divisions
-        if (ch + 1 == nchunks) { pst->ch = 0; pst->J = J + 1; } else pst->ch = ch + 1;
+        if (ch + 1 == nchunks) { pst->ch = 0; pst->J = J + NCT; } else pst->ch = ch + 1;
+        const bool second = (NCT == 2) && (J + 1 < pst->jend);
         const int w0 = ch * KW;
         const int nw = min(KW, p.W - w0);
         m.ti = ti; m.J = J; m.w0 = w0; m.nw = nw;
         m.flags = (ch == 0 ? PKF_FIRST_J : 0) | (ch == nchunks - 1 ? PKF_LAST_J : 0) |
-                  (st == pst->nsteps - 1 ? PKF_LAST_ITEM : 0);
+                  (st == pst->nsteps - 1 ? PKF_LAST_ITEM : 0) | (second ? PKF_SECOND : 0);
         uint32_t* dst = stages + (size_t)slot * stage_words;
-        mbar_expect_tx(&full[slot], (uint32_t)nw * 2u * op_bytes);
+        mbar_expect_tx(&full[slot], (uint32_t)nw * (second ? 3u : 2u) * op_bytes);
         const uint32_t* rbase = p.row_planes + (size_t)ti * tile_stride;
         const uint32_t* cbase = p.col_planes + (size_t)J * tile_stride;
         // one bulk copy per run of consecutive staged words (the whole step when the order is contiguous)
@@ -237,31 +254,33 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
             while (kk + run < nw && word_of(w0 + kk + run) == w + run) ++run;
             bulk_g2s(dst + kk * op_words, rbase + (size_t)w * word_stride, (uint32_t)run * op_bytes, &full[slot]);
             bulk_g2s(dst + (KW + kk) * op_words, cbase + (size_t)w * word_stride, (uint32_t)run * op_bytes, &full[slot]);
+            if (second)
+                bulk_g2s(dst + (2 * KW + kk) * op_words, cbase + tile_stride + (size_t)w * word_stride, (uint32_t)run * op_bytes, &full[slot]);
             kk += run;
         }
         pst->step = st + 1; pst->count = pr_count + 1;
     };
     if (tid == 0) {
-        pst->count = 0; pst->step = 0; pst->nsteps = 0; pst->ti = 0; pst->J = 0; pst->ch = 0; pst->done = 0;
+        pst->count = 0; pst->step = 0; pst->nsteps = 0; pst->ti = 0; pst->J = 0; pst->ch = 0; pst->done = 0; pst->jend = 0;
         for (int s = 0; s < PK_NS; ++s) { slot_cnt[s] = 0; produce_one(); }
     }
     __syncthreads();
 
     // ---- consumers (all 8 warps) ----
     // Accumulators count in units of 4 (acc = 4 * count [+ carried class offset]).
-    uint32_t acc[4][4];
-    int gj[4];
-    int sgn[4];
+    uint32_t acc[4][NB];
+    int gj[NB];
+    int sgn[NB];
     uint32_t om = 0u;          // tie-coin orientation [i<j] of this thread's pairs (all-ones / zero) ...
-    uint32_t obits = 0u;       // ... and per pair (bit a*4+b), used only when the 4x4 block straddles i == j
+    uint32_t obits = 0u;       // ... and per pair (bit a*NB+b), used only when the 4xNB block straddles i == j
     bool uniform = true, all_valid = false;
     int gi0 = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0u;
+        for (int b = 0; b < NB; ++b) acc[a][b] = 0u;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) { gj[b] = -1; sgn[b] = 1; }
+    for (int b = 0; b < NB; ++b) { gj[b] = -1; sgn[b] = 1; }
     const uint32_t four = p.one << 2;
     const uint32_t lut_s = smem_u32(lut);
     const uint32_t tab_row_s = smem_u32(tab_s) + (uint32_t)(ty * 4) * 4u;   // + bin*256 + a*4
@@ -297,19 +316,31 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
                 const char4 s4 = *reinterpret_cast<const char4*>(p.col_sign + m.J * REO_TILE + tx * 4);
                 sgn[0] = s4.x; sgn[1] = s4.y; sgn[2] = s4.z; sgn[3] = s4.w;
             }
-            // columns ascend.  Orientation [i<j] is uniform over the 4x4 block unless it straddles i == j.
-            const bool cols_ok = (gj[0] >= 0) && (gj[3] >= 0);
+            if (NB == 8) {   // second column tile of the step (absent at the end of an odd chunk: pad columns)
+                if (m.flags & PKF_SECOND) {
+                    const int4 h4 = *reinterpret_cast<const int4*>(p.col_gene + (m.J + 1) * REO_TILE + tx * 4);
+                    gj[NB - 4] = h4.x; gj[NB - 3] = h4.y; gj[NB - 2] = h4.z; gj[NB - 1] = h4.w;
+                    if (p.col_sign) {
+                        const char4 s4 = *reinterpret_cast<const char4*>(p.col_sign + (m.J + 1) * REO_TILE + tx * 4);
+                        sgn[NB - 4] = s4.x; sgn[NB - 3] = s4.y; sgn[NB - 2] = s4.z; sgn[NB - 1] = s4.w;
+                    }
+                } else {
+                    gj[NB - 4] = -1; gj[NB - 3] = -1; gj[NB - 2] = -1; gj[NB - 1] = -1;
+                }
+            }
+            // columns ascend.  Orientation [i<j] is uniform over the 4xNB block unless it straddles i == j.
+            const bool cols_ok = (gj[0] >= 0) && (gj[NB - 1] >= 0);
             const bool all_lt = cols_ok && (gi0 + 3 < gj[0]);     // every row index below every column index
-            const bool all_ge = cols_ok && (gi0 > gj[3]);         // every row index above every column index
+            const bool all_ge = cols_ok && (gi0 > gj[NB - 1]);    // every row index above every column index
             uniform = all_lt || all_ge;
             all_valid = uniform && (gi0 + 3 < p.r);
             om = all_lt ? 0xffffffffu : 0u;
-            obits = all_lt ? 0xffffu : 0u;
+            obits = all_lt ? (NB == 8 ? 0xffffffffu : 0xffffu) : 0u;
             if (!uniform) {
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) obits |= (uint32_t)(gi0 + a < gj[b]) << (a * 4 + b);
+                    for (int b = 0; b < NB; ++b) obits |= (uint32_t)(gi0 + a < gj[b]) << (a * NB + b);
                 om = (obits & 1u) ? 0xffffffffu : 0u;
             }
             if (LUT) {
@@ -317,18 +348,18 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = a0;
+                    for (int b = 0; b < NB; ++b) acc[a][b] = a0;
                 if (!uniform) {
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = lut_s + ((obits >> (a * 4 + b)) & 1u) * (uint32_t)(SZA * 4);
+                        for (int b = 0; b < NB; ++b) acc[a][b] = lut_s + ((obits >> (a * NB + b)) & 1u) * (uint32_t)(SZA * 4);
                 }
             } else {
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = 0u;
+                    for (int b = 0; b < NB; ++b) acc[a][b] = 0u;
             }
         }
         const uint32_t* srow = stages + (size_t)slot * stage_words;
@@ -340,11 +371,12 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = flushA(acc[a][b], a * 4 + b);
+                    for (int b = 0; b < NB; ++b) acc[a][b] = flushA(acc[a][b], a * NB + b);
             }
             const uint32_t* xr = srow + kk * op_words + ty * 4;
             const uint32_t* yc = scol + kk * op_words + tx * 4;
-            uint32_t bor[4][4];
+            const uint32_t* yc2 = yc + KW * op_words;     // second column tile (NB == 8)
+            uint32_t bor[4][NB];
             if (FLT) {
                 // raw-value path: per sample d = x - y; "greater" iff d >= 0.1, tie iff -0.1 < d < 0.1
                 // (== abs(x - y) < 0.1 ? coin : x > y, src:72-76), 32 samples -> two bit masks per pair
@@ -380,21 +412,26 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
+                    for (int b = 0; b < 4; ++b) {     // the raw-value path is instantiated with NB == 4 only
                         uint32_t coin = xc[a] ^ yw[b] ^ om;
-                        if (!uniform) coin ^= (0u - (((obits >> (a * 4 + b)) ^ obits) & 1u));
+                        if (!uniform) coin ^= (0u - (((obits >> (a * NB + b)) ^ obits) & 1u));
                         bor[a][b] = gtm[a][b] | (lem[a][b] & ~gtm[a][b] & coin);
                     }
             } else {
-            {
+                {
                     const uint4 xv = *reinterpret_cast<const uint4*>(xr);
                     const uint4 yv = *reinterpret_cast<const uint4*>(yc);
                     const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+                    uint32_t y[NB];
+                    y[0] = yv.x; y[1] = yv.y; y[2] = yv.z; y[3] = yv.w;
+                    if (NB == 8) {
+                        const uint4 zv = *reinterpret_cast<const uint4*>(yc2);
+                        y[NB - 4] = zv.x; y[NB - 3] = zv.y; y[NB - 2] = zv.z; y[NB - 1] = zv.w;
+                    }
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) bor[a][b] = lop3_xor3(x[a], y[b], om);
+                        for (int b = 0; b < NB; ++b) bor[a][b] = lop3_xor3(x[a], y[b], om);
                 }
                 if (!uniform) {   // rare: flip the coin seed of the pairs whose orientation differs from pair (0,0)
                     uint32_t ob = obits;
@@ -402,7 +439,7 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) bor[a][b] ^= (0u - (((ob >> (a * 4 + b)) ^ ob) & 1u));
+                        for (int b = 0; b < NB; ++b) bor[a][b] ^= (0u - (((ob >> (a * NB + b)) ^ ob) & 1u));
                 }
                 if (NPT > 0) {
 #pragma unroll
@@ -410,11 +447,16 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
                         const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
                         const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
                         const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                        const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+                        uint32_t y[NB];
+                        y[0] = yv.x; y[1] = yv.y; y[2] = yv.z; y[3] = yv.w;
+                        if (NB == 8) {
+                            const uint4 zv = *reinterpret_cast<const uint4*>(yc2 + pl * REO_TILE);
+                            y[NB - 4] = zv.x; y[NB - 3] = zv.y; y[NB - 2] = zv.z; y[NB - 1] = zv.w;
+                        }
 #pragma unroll
                         for (int a = 0; a < 4; ++a)
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                            for (int b = 0; b < NB; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
                     }
                 } else {
 #pragma unroll 2
@@ -422,11 +464,16 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
                         const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
                         const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
                         const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                        const uint32_t y[4] = {yv.x, yv.y, yv.z, yv.w};
+                        uint32_t y[NB];
+                        y[0] = yv.x; y[1] = yv.y; y[2] = yv.z; y[3] = yv.w;
+                        if (NB == 8) {
+                            const uint4 zv = *reinterpret_cast<const uint4*>(yc2 + pl * REO_TILE);
+                            y[NB - 4] = zv.x; y[NB - 3] = zv.y; y[NB - 2] = zv.z; y[NB - 1] = zv.w;
+                        }
 #pragma unroll
                         for (int a = 0; a < 4; ++a)
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                            for (int b = 0; b < NB; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
                     }
                 }
             }
@@ -436,15 +483,15 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
+                    for (int b = 0; b < NB; ++b) {
                         const uint32_t fullA = mad_acc((uint32_t)__popc(bor[a][b] & p.maskA), four, acc[a][b]);
-                        acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b] & p.maskB), four, flushA(fullA, a * 4 + b));
+                        acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b] & p.maskB), four, flushA(fullA, a * NB + b));
                     }
             } else {
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b]), four, acc[a][b]);
+                    for (int b = 0; b < NB; ++b) acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b]), four, acc[a][b]);
             }
         }
         if (m.flags & PKF_LAST_J) {
@@ -453,8 +500,8 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const uint32_t addr = tab_row_s + binB(acc[a][b], a * 4 + b) + (uint32_t)(a * 4);
+                    for (int b = 0; b < NB; ++b) {
+                        const uint32_t addr = tab_row_s + binB(acc[a][b], a * NB + b) + (uint32_t)(a * 4);
                         asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(sgn[b]) : "memory");
                     }
             } else {   // pad columns, rows beyond r, self pairs: only on the matrix edges and the diagonal
@@ -462,8 +509,8 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : PK_CTAS_PER_SM) reo_pair
                 for (int a = 0; a < 4; ++a) {
                     const int gi = gi0 + a;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const uint32_t off = binB(acc[a][b], a * 4 + b);
+                    for (int b = 0; b < NB; ++b) {
+                        const uint32_t off = binB(acc[a][b], a * NB + b);
                         if (gj[b] >= 0 && gi != gj[b] && gi < p.r) {
                             const uint32_t addr = tab_row_s + off + (uint32_t)(a * 4);
                             asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(sgn[b]) : "memory");
@@ -499,37 +546,42 @@ static void pair_lut_sizes(const ReoPairParams& p, int* sza, int* szb, int* use)
     *sza = a; *szb = b;
     *use = (2 * a + 6 * b) <= PK_LUT_MAX_WORDS;
 }
-static int pair_kw(int NP, int W, int lut_words) {
-    int kw = (PK_SMEM_BUDGET - lut_words * 4) / (PK_NS * 2 * NP * REO_TILE * 4);
+// nct = column tiles per step (1, or 2 for the 4x8 register tile)
+static int pair_kw(int NP, int W, int lut_words, int nct) {
+    int kw = ((nct == 2 ? PK_SMEM_BUDGET_NB : PK_SMEM_BUDGET) - lut_words * 4) / (PK_NS * (1 + nct) * NP * REO_TILE * 4);
     if (kw > PK_MAX_KW) kw = PK_MAX_KW;
     if (kw > W) kw = W;
     if (kw < 1) kw = 1;
     const int nsteps = (W + kw - 1) / kw;   // spread the words evenly over the steps of one column tile
     return (W + nsteps - 1) / nsteps;
 }
-static size_t pair_smem_bytes(int NP, int KW, int lut_words) {
-    return (size_t)PK_NS * 2 * KW * NP * REO_TILE * 4 + REO_TILE * 9 * 4 + PK_NS * sizeof(PkMeta) + PK_NS * 8 +
+static size_t pair_smem_bytes(int NP, int KW, int lut_words, int nct) {
+    return (size_t)PK_NS * (1 + nct) * KW * NP * REO_TILE * 4 + REO_TILE * 9 * 4 + PK_NS * sizeof(PkMeta) + PK_NS * 8 +
            sizeof(PkProd) + PK_NS * 4 + (size_t)lut_words * 4 + 16;
 }
 
 template <int NPT, bool LUT, bool FLT = false>
 static cudaError_t launch_np_lut(const ReoPairParams& p, int lut_words, int num_sms, cudaStream_t st) {
-    const size_t smem = pair_smem_bytes(FLT ? REO_FLT_OPWORDS / REO_TILE : p.NP, p.KW, lut_words);
-    cudaError_t e = cudaFuncSetAttribute(reo_pair_kernel<NPT, LUT, FLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int NB = FLT ? 4 : PK_NB;
+    const size_t smem = pair_smem_bytes(FLT ? REO_FLT_OPWORDS / REO_TILE : p.NP, p.KW, lut_words, NB / 4);
+    cudaError_t e = cudaFuncSetAttribute(reo_pair_kernel<NPT, LUT, FLT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nitems = (p.t1 - p.t0) * p.njchunks;
-    int grid = PK_CTAS_PER_SM * num_sms;
+    int grid = (NB == 8 ? 2 : PK_CTAS_PER_SM) * num_sms;
     if (grid > nitems) grid = nitems;
     if (grid < 1) return cudaSuccess;
-    reo_pair_kernel<NPT, LUT, FLT><<<grid, PK_THREADS, smem, st>>>(p);
+    reo_pair_kernel<NPT, LUT, FLT, NB><<<grid, PK_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
+
+// column tiles one step of the rank-path kernel consumes: chunks of column tiles should be multiples of it
+int reo_pairs_col_tiles_per_step(bool flt) { return flt ? 1 : PK_NB / 4; }
 
 template <int NPT>
 static cudaError_t launch_np(ReoPairParams p, int num_sms, cudaStream_t st) {
     pair_lut_sizes(p, &p.lutSZA, &p.lutSZB, &p.use_lut);
     const int lut_words = p.use_lut ? 2 * p.lutSZA + 6 * p.lutSZB : 0;
-    p.KW = pair_kw(p.NP, p.W, lut_words);
+    p.KW = pair_kw(p.NP, p.W, lut_words, PK_NB / 4);
     p.one = 1u;
     return p.use_lut ? launch_np_lut<NPT, true>(p, lut_words, num_sms, st)
                      : launch_np_lut<NPT, false>(p, lut_words, num_sms, st);
@@ -541,7 +593,7 @@ cudaError_t reo_launch_pairs(const ReoPairParams& p, int num_sms, cudaStream_t s
         ReoPairParams q = p;
         pair_lut_sizes(q, &q.lutSZA, &q.lutSZB, &q.use_lut);
         const int lut_words = q.use_lut ? 2 * q.lutSZA + 6 * q.lutSZB : 0;
-        q.KW = pair_kw(REO_FLT_OPWORDS / REO_TILE, q.W, lut_words);
+        q.KW = pair_kw(REO_FLT_OPWORDS / REO_TILE, q.W, lut_words, 1);
         q.one = 1u;
         return q.use_lut ? launch_np_lut<0, true, true>(q, lut_words, num_sms, st)
                          : launch_np_lut<0, false, true>(q, lut_words, num_sms, st);
