@@ -18,18 +18,19 @@
 // triples.  The ALU (LOP3) pipe is the roofline; no tensor cores.
 //
 // Tiling: CTA = 64 row genes x 64 column genes, 256 threads, 4x4 pairs per thread (16 independent
-// borrow chains per thread hide the 4-cycle ALU latency).  Operand tiles ([plane][64 genes] words)
-// are streamed by cp.async.bulk (UBLKCP) into a 4-slot shared-memory ring guarded by mbarriers
-// with transaction counts; the warp that is LAST to finish a slot refills it, so no warp ever
-// waits on an "empty" barrier and there is no CTA-wide barrier in the loop.  Each thread reads its
-// 4 row words and 4 column words per plane with two LDS.128 (bank-conflict free).
+// borrow chains per thread hide the 4-cycle ALU latency); -DPK_NB=8 builds the 4x8 variant (two column
+// tiles per step).  Operand tiles ([plane][64 genes] words) are streamed by cp.async.bulk (UBLKCP) into
+// a 2-slot shared-memory ring (up to 8 sample words per slot) guarded by mbarriers with transaction
+// counts; the warp that is LAST to finish a slot refills it, so no warp ever waits on an "empty"
+// barrier and there is no CTA-wide barrier in the loop.  Each thread reads its 4 row words and 4 column
+// words per plane with two LDS.128 (bank-conflict free).
 // Classification: accumulators count in units of 4, i.e. they ARE byte offsets into small
 // shared-memory lookup tables that turn (count of group A) -> class offset and
 // (class of A, count of group B) -> table bin, so the per-pair epilogue costs loads, not ALU ops
 // (compare-based fallback when the tables would not fit, i.e. thousands of samples per group,
 // where the epilogue is negligible anyway).
 // Work items (row tile x chunk of column tiles) are handed out by an atomic counter to a
-// persistent grid of 2 CTAs per SM; each item accumulates a 9 x 64 table in shared memory and
+// persistent grid of 3 CTAs per SM; each item accumulates a 9 x 64 table in shared memory and
 // flushes it with integer atomics (order independent, exact).
 #include "reo_internal.cuh"
 
