@@ -87,8 +87,8 @@ struct ReoDev {
     DBuf<uint16_t> ranks;
     DBuf<uint32_t> planes, panel, k1_send, k1_gather;
     DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, perm2, counts,
-        fblist, widelist, small_i, stage_lists;
-    DBuf<int8_t> changed_sign, updown;
+        fblist, widelist, small_i, stage_lists, table_red, table_all, list_gene;
+    DBuf<int8_t> changed_sign, updown, list_sign;
     DBuf<uint8_t> mask_a, mask_b;
     DBuf<double> result, sorted, sorted_p, se, small_d, std_ws;
     DBuf<unsigned int> counter;
@@ -101,7 +101,8 @@ struct ReoDev {
     uint8_t* h_out = nullptr;     // pinned staging for results (grow-only)
     size_t h_out_cap = 0;
     bool early_pending = false;   // a copy of result columns 2..14 is in flight on st_copy (ev[7] marks its end)
-    int table_rows = 0;           // rows allocated in `table`
+    int32_t* table_cur = nullptr; // tables the statistics read: `table` (one rank) or `table_red` (sum over ranks)
+    int64_t list_cap = 0;         // entries of the gene lists (col_gene, changed_*, list_*, iota)
     std::vector<cudaEvent_t> pev; // event pairs bracketing every pair-kernel launch of the current call
     int n_pev = 0;
     int64_t iota_r = -1;
@@ -470,35 +471,72 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         CKL(reo_launch_unshard_planes(D.k1_gather.p, S.planes, S.NT, W, wq, (int)wb, D.st));
         h->kernel_launches += 2;
     }
-    // identity column list for "all genes are references" (cached while r is unchanged)
+    // gene lists are padded with -1 up to whole T-tile blocks plus a pair of tiles (the pair kernel copies the ids of
+    // two column tiles per step); identity list for "all genes are references" (cached while r is unchanged)
+    const int64_t list_cap = rpad + (int64_t)(8 + 8 + 2) * REO_TILE;
+    D.list_cap = list_cap;
     if (D.iota_r != r) {
-        std::vector<int32_t> iota(rpad, -1);
+        std::vector<int32_t> iota(list_cap, -1);
         for (int64_t i = 0; i < r; ++i) iota[i] = (int32_t)i;
-        CK(D.iota.ensure(rpad));
-        CK(cudaMemcpyAsync(D.iota.p, iota.data(), rpad * 4, cudaMemcpyHostToDevice, D.st));
+        CK(D.iota.ensure(list_cap));
+        CK(cudaMemcpyAsync(D.iota.p, iota.data(), list_cap * 4, cudaMemcpyHostToDevice, D.st));
         CK(cudaStreamSynchronize(D.st));  // iota is a host temporary
         D.iota_r = r;
     }
-    CK(D.col_gene.ensure(rpad));
-    CK(D.changed_gene.ensure(rpad));
-    CK(D.changed_sign.ensure(rpad));
+    CK(D.col_gene.ensure(list_cap));
+    CK(D.changed_gene.ensure(list_cap));
+    CK(D.changed_sign.ensure(list_cap));
+    CK(D.list_gene.ensure(list_cap));
+    CK(D.list_sign.ensure(list_cap));
     CK(D.counts.ensure(8));
     CK(D.counter.ensure(1));
     CK(D.mask_a.ensure(r));
     CK(D.mask_b.ensure(r));
-    // table: world * tiles_per_rank * 64 rows so that the all-gather slices are equal
-    const int tpr = (S.NT + h->world - 1) / h->world;
-    D.table_rows = h->world * tpr * REO_TILE;
-    CK(D.table.ensure((size_t)D.table_rows * 9));
+    // table: this rank's partial sums (r x 9); with several ranks the statistics read the sum over ranks
+    CK(D.table.ensure((size_t)r * 9));
+    D.table_cur = D.table.p;
+    if (h->world > 1) {
+        CK(D.table_red.ensure((size_t)r * 9));
+        D.table_cur = D.table_red.p;
+        if (!D.comm) CK(D.table_all.ensure((size_t)h->world * r * 9));
+    }
     S.valid = true;
     return REO_OK;
 }
 
 // ---- K2 launches --------------------------------------------------------------------------------
-// Accumulate sign * category counts of every row gene of this rank's shard against `ncols` panel
-// columns listed (ascending, padded to 64 with -1) in col_gene_dev.
-int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* col_gene_dev,
-                  const int8_t* col_sign_dev, int ncols, bool all_genes) {
+bool pairs_v1() {   // REO_PAIRS_V1=1: first-generation pair kernel on the rank path too (A/B comparisons)
+    static const bool v = [] { const char* e = getenv("REO_PAIRS_V1"); return e && e[0] && e[0] != '0'; }();
+    return v;
+}
+// a column set of n genes is worth the symmetric treatment (permuted panel [C ; N]) from this size on
+bool sym_worth(int64_t n, int64_t r) { return n >= 1024 && n * 8 >= r; }
+// relative cost (pair evaluations) of accumulating n columns into the tables of r genes
+double tables_cost(int64_t n, int64_t r, bool flt) {
+    if (!flt && !pairs_v1() && (n == r || sym_worth(n, r))) return (double)n * ((double)r - 0.5 * (double)n);
+    return (double)n * (double)r;
+}
+
+int record_pair_events(reo_handle_t h, ReoDev& D, bool begin) {
+    if (begin && (size_t)(2 * D.n_pev + 2) > D.pev.size()) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        D.pev.push_back(a); D.pev.push_back(b);
+    }
+    CK(cudaEventRecord(D.pev[2 * D.n_pev + (begin ? 0 : 1)], D.st));
+    if (!begin) { D.n_pev++; h->pair_launches++; h->kernel_launches++; }
+    return REO_OK;
+}
+
+// this rank's share of `total` executed comparisons (the shares of all ranks add up to total)
+int64_t rank_share(reo_handle_t h, int64_t total) {
+    return total / h->world + (h->rank < (int)(total % h->world) ? 1 : 0);
+}
+
+// First-generation kernel (raw-FP64 variant; REO_PAIRS_V1): every row gene of this rank's row-tile shard against the
+// `ncols` panel columns listed (ascending, padded with -1) in col_gene_dev.
+int launch_tables_v1(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* col_gene_dev,
+                     const int8_t* col_sign_dev, int ncols, bool all_genes) {
     const ReoStaged& S = D.S;
     if (ncols <= 0) return REO_OK;
     const int ntc = (ncols + REO_TILE - 1) / REO_TILE;
@@ -535,49 +573,118 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_t* 
     p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;
     p.flt = S.flt ? 1 : 0;
     CK(cudaMemsetAsync(D.counter.p, 0, sizeof(unsigned int), D.st));
-    if ((size_t)(2 * D.n_pev + 2) > D.pev.size()) {
-        cudaEvent_t a, b;
-        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-        D.pev.push_back(a); D.pev.push_back(b);
-    }
-    CK(cudaEventRecord(D.pev[2 * D.n_pev], D.st));
+    int rc = record_pair_events(h, D, true);
+    if (rc) return rc;
     CKL(reo_launch_pairs(p, D.num_sms, D.st));
-    CK(cudaEventRecord(D.pev[2 * D.n_pev + 1], D.st));
-    D.n_pev++;
-    h->pair_launches++; h->kernel_launches++;
+    if ((rc = record_pair_events(h, D, false))) return rc;
     const int64_t rows = std::min<int64_t>(S.r, (int64_t)p.t1 * REO_TILE) - (int64_t)p.t0 * REO_TILE;
     h->compares += std::max<int64_t>(rows, 0) * (int64_t)ncols * S.c;
+    return REO_OK;
+}
+
+// Accumulate sign(j) * e(category(i, j)) into the table of every gene i, for the column set C of `ncols` genes:
+//   m_new == nullptr : C = { j : m_old[j] }, all signs +1 (full build for the reference set m_old);
+//   m_new != nullptr : C = m_old xor m_new, sign +1 for genes that enter the set and -1 for genes that leave it
+//                      (incremental update; mask_diff has left the list in changed_gene / changed_sign).
+// Three shapes (v2 kernel): every gene is a column -> symmetric sweep over the staged planes themselves; a large C ->
+// permuted panel [C ; N], symmetric C x C plus one-sided N x C; a small C -> one-sided, all genes x gathered C.
+int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* m_old, const uint8_t* m_new, int ncols) {
+    const ReoStaged& S = D.S;
+    if (ncols <= 0) return REO_OK;
+    const bool all = (m_new == nullptr && ncols == (int)S.r);
+    if (S.flt || pairs_v1()) {
+        if (all) return launch_tables_v1(h, D, P, D.iota.p, nullptr, ncols, true);
+        if (m_new) return launch_tables_v1(h, D, P, D.changed_gene.p, D.changed_sign.p, ncols, false);
+        CKL(reo_launch_mask_to_list(m_old, S.r, D.col_gene.p, D.counts.p + 4, D.st));
+        h->kernel_launches++;
+        return launch_tables_v1(h, D, P, D.col_gene.p, nullptr, ncols, false);
+    }
+    const int T = reo_pairs2_block_edge(S.W, S.NP);
+    ReoPair2Params p;
+    memset(&p, 0, sizeof(p));
+    p.T = T; p.rank = h->rank; p.world = h->world;
+    p.segA0 = P.segA0; p.mixedW = P.mixedW; p.segB0 = P.segB0; p.segB0len = P.segB0len; p.segB1 = P.segB1;
+    p.table = D.table.p; p.counter = D.counter.p;
+    p.W = S.W; p.WA = P.WA; p.NP = S.NP;
+    p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
+    p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;
+    const int64_t rr = S.r, nc = ncols;
+    int64_t executed;   // pair evaluations x samples actually needed (self pairs and pads excluded)
+    if (all) {
+        p.row_planes = p.col_planes = S.planes;
+        p.row_gene = p.col_gene = D.iota.p;
+        p.ntr = p.ntc = p.nsym = S.NT;
+        executed = rr * (rr - 1) / 2 * S.c;
+    } else if (sym_worth(nc, rr)) {
+        const int ntc = (ncols + REO_TILE - 1) / REO_TILE;
+        const int nsymp = (ntc + T - 1) / T * T;
+        const int ntn = (int)((rr - nc + REO_TILE - 1) / REO_TILE);
+        CKL(reo_launch_sym_lists(S.r, m_old, m_new, T, D.list_gene.p, D.list_sign.p, D.counts.p + 5, D.list_cap, D.st));
+        CK(D.panel.ensure((size_t)(nsymp + ntn + 1) * S.tile_stride()));
+        CKL(reo_launch_gather_panel(S.planes, S.W, S.NP, D.list_gene.p, nsymp + ntn, D.panel.p, D.st));
+        h->kernel_launches += 2;
+        p.row_planes = p.col_planes = D.panel.p;
+        p.row_gene = p.col_gene = D.list_gene.p;
+        p.row_sign = p.col_sign = m_new ? D.list_sign.p : nullptr;
+        p.ntr = nsymp + ntn; p.ntc = p.nsym = ntc;
+        executed = (nc * (nc - 1) / 2 + (rr - nc) * nc) * S.c;
+    } else {
+        const int ntc = (ncols + REO_TILE - 1) / REO_TILE;
+        const int32_t* cg = D.changed_gene.p;
+        if (!m_new) {
+            CKL(reo_launch_mask_to_list(m_old, S.r, D.col_gene.p, D.counts.p + 4, D.st));
+            h->kernel_launches++;
+            cg = D.col_gene.p;
+        }
+        CK(D.panel.ensure((size_t)(ntc + 1) * S.tile_stride()));
+        CKL(reo_launch_gather_panel(S.planes, S.W, S.NP, cg, ntc, D.panel.p, D.st));
+        h->kernel_launches++;
+        p.row_planes = S.planes; p.col_planes = D.panel.p;
+        p.row_gene = D.iota.p; p.col_gene = cg;
+        p.col_sign = m_new ? D.changed_sign.p : nullptr;
+        p.ntr = S.NT; p.ntc = ntc; p.nsym = 0;
+        executed = (rr * nc - nc) * S.c;
+    }
+    CK(cudaMemsetAsync(D.counter.p, 0, sizeof(unsigned int), D.st));
+    int rc = record_pair_events(h, D, true);
+    if (rc) return rc;
+    CKL(reo_launch_pairs2(p, D.num_sms, D.st));
+    if ((rc = record_pair_events(h, D, false))) return rc;
+    h->compares += rank_share(h, executed);
     return REO_OK;
 }
 
 // full build for the mask in mask_dev; ncols = its population count when the host already knows it (-1: read it back)
 int build_tables_full(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* mask_dev, int ncols = -1) {
     const ReoStaged& S = D.S;
-    CKL(reo_launch_mask_to_list(mask_dev, S.r, D.col_gene.p, D.counts.p + 4, D.st));
-    h->kernel_launches++;
-    CK(cudaMemsetAsync(D.table.p, 0, (size_t)D.table_rows * 9 * sizeof(int32_t), D.st));
+    CK(cudaMemsetAsync(D.table.p, 0, (size_t)S.r * 9 * sizeof(int32_t), D.st));
     if (ncols < 0) {
+        CKL(reo_launch_mask_to_list(mask_dev, S.r, D.col_gene.p, D.counts.p + 4, D.st));
+        h->kernel_launches++;
         CK(cudaMemcpyAsync(D.h_counts + 4, D.counts.p + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
         ncols = D.h_counts[4];
     }
-    const bool all = (ncols == (int)S.r);
-    return launch_tables(h, D, P, all ? D.iota.p : D.col_gene.p, nullptr, ncols, all);
+    return launch_tables(h, D, P, mask_dev, nullptr, ncols);
 }
 
-int allgather_tables(reo_handle_t h, ReoDev& D) {
+// Several ranks: every rank holds partial sums for ALL genes (its share of the pair tiles); the statistics read
+// their sum.  NCCL all-reduce on the library's stream, or the user's all-gather callback followed by a local sum.
+int reduce_tables(reo_handle_t h, ReoDev& D) {
     if (h->world <= 1) return REO_OK;
-    if (D.comm) {  // NCCL over NVLink, in place, ordered on the library's stream (no host synchronisation)
-        const size_t count = (size_t)(D.table_rows / h->world) * 9;
-        ncclResult_t nr = g_nccl.AllGather(D.table.p + (size_t)h->rank * count, D.table.p, count, ncclInt32, D.comm, D.st);
-        if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclAllGather: ") + g_nccl.GetErrorString(nr));
+    const size_t n = (size_t)D.S.r * 9;
+    if (D.comm) {
+        ncclResult_t nr = g_nccl.AllReduce(D.table.p, D.table_red.p, n, ncclInt32, ncclSum, D.comm, D.st);
+        if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(nr));
         h->kernel_launches++;
         return REO_OK;
     }
     if (!h->ag_fn) return fail(h, REO_ERR_COMM, "world > 1 but neither an NCCL communicator nor an all-gather callback is set");
+    CK(cudaMemcpyAsync(D.table_all.p + (size_t)h->rank * n, D.table.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, D.st));
     CK(cudaStreamSynchronize(D.st));
-    const uint64_t bytes = (uint64_t)(D.table_rows / h->world) * 9 * sizeof(int32_t);
-    if (h->ag_fn(h->ag_ctx, D.table.p, bytes) != 0) return fail(h, REO_ERR_COMM, "all-gather callback failed");
+    if (h->ag_fn(h->ag_ctx, D.table_all.p, (uint64_t)n * sizeof(int32_t)) != 0) return fail(h, REO_ERR_COMM, "all-gather callback failed");
+    CKL(reo_launch_sum_slices(D.table_all.p, h->world, (int64_t)n, D.table_red.p, D.st));
+    h->kernel_launches++;
     return REO_OK;
 }
 
@@ -587,7 +694,7 @@ int allgather_tables(reo_handle_t h, ReoDev& D) {
 // image of `result` for this level, pinned).
 int enqueue_mcc(reo_handle_t h, ReoDev& D, int64_t r, double* early_dst) {
     if (D.early_pending) CK(cudaStreamWaitEvent(D.st, D.ev[7], 0));   // the previous copy still reads `result`
-    CKL(reo_launch_mccullagh_tables(D.table.p, r, D.result.p, D.st));
+    CKL(reo_launch_mccullagh_tables(D.table_cur, r, D.result.p, D.st));
     if (early_dst) {
         CK(cudaEventRecord(D.ev[6], D.st));
         CK(cudaStreamWaitEvent(D.st_copy, D.ev[6], 0));
@@ -628,7 +735,7 @@ int run_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double padj_
     const int rc0 = enqueue_mcc(h, D, r, early_dst);
     if (rc0 != REO_OK) return rc0;
     if (debug_sync() || no_graph) return enqueue_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new);
-    const std::vector<const void*> key = {D.table.p, D.result.p, D.sorted.p, D.perm.p, D.sorted_p.p, D.perm2.p, D.se.p,
+    const std::vector<const void*> key = {D.table_cur, D.result.p, D.sorted.p, D.perm.p, D.sorted_p.p, D.perm2.p, D.se.p,
                                           D.counts.p, D.changed_gene.p, D.changed_sign.p, D.sortws.keys, D.std_ws.p,
                                           D.mask_a.p, D.mask_b.p, D.h_counts};
     if (key != D.eval_key || r != D.eval_r || pval_deg != D.eval_pd || padj_deg != D.eval_qd) {
@@ -791,6 +898,7 @@ int reo_destroy(reo_handle_t h) {
         if (D.st) cudaStreamSynchronize(D.st);
         if (D.comm) { g_nccl.CommDestroy(D.comm); D.comm = nullptr; }
         drop_eval_graphs(D);
+        D.table_red.release(); D.table_all.release(); D.list_gene.release(); D.list_sign.release();
         D.k1_send.release(); D.k1_gather.release(); D.stage_lists.release(); D.widelist.release();
         D.raw.release(); D.raw2.release(); D.pb.release(); D.sub.release(); D.ranks.release(); D.planes.release(); D.panel.release(); D.slot_of_sample.release();
         D.sample_of_slot.release(); D.word_order.release(); D.iota.release(); D.col_gene.release();
@@ -924,10 +1032,10 @@ int reo_tables_delta(reo_handle_t h, int32_t k, const int32_t* thresholds, doubl
         CKL(reo_launch_mask_diff(S.r, D.mask_a.p, D.mask_b.p, D.counts.p, D.changed_gene.p, D.changed_sign.p, D.st));
         CK(cudaMemcpyAsync(D.h_counts, D.counts.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
-        if ((rc = launch_tables(h, D, P, D.changed_gene.p, D.changed_sign.p, D.h_counts[2], false))) return rc;
+        if ((rc = launch_tables(h, D, P, D.mask_a.p, D.mask_b.p, D.h_counts[2]))) return rc;
     }
-    if ((rc = allgather_tables(h, D))) return rc;
-    CK(cudaMemcpyAsync(table, D.table.p, (size_t)S.r * 9 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+    if ((rc = reduce_tables(h, D))) return rc;
+    CK(cudaMemcpyAsync(table, D.table_cur, (size_t)S.r * 9 * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
     return REO_OK;
 }
@@ -1180,7 +1288,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
                 if ((rc = build_tables_full(h, D, P, mask_cur, n0))) return rc;
                 have_tables = true;
             }
-            if ((rc = allgather_tables(h, D))) return rc;
+            if ((rc = reduce_tables(h, D))) return rc;
             static const bool timing = getenv("REO_TIMING") != nullptr;
             if (timing) CK(cudaEventRecord(D.ev[3], D.st));
             if ((rc = run_eval(h, D, r, pval_deg, padj_deg, mask_cur, mask_new, res_host + (size_t)k * r * 15))) return rc;
@@ -1202,8 +1310,8 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             if (i_iter < n_iter) {
                 // tables for the new reference set: signed update over the symmetric difference when
                 // that is cheaper than a rebuild (the G x G categories are never stored)
-                if (n_chg < n_inds) {
-                    if ((rc = launch_tables(h, D, P, D.changed_gene.p, D.changed_sign.p, n_chg, false))) return rc;
+                if (tables_cost(n_chg, r, S.flt) < tables_cost(n_inds, r, S.flt)) {
+                    if ((rc = launch_tables(h, D, P, mask_cur, mask_new, n_chg))) return rc;
                     std::swap(mask_cur, mask_new);
                 } else {
                     std::swap(mask_cur, mask_new);

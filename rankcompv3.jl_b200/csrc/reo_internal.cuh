@@ -77,6 +77,40 @@ struct ReoPairParams {
     unsigned int one;            // == 1 (see mad_acc in reo_pairs.cu)
 };
 
+// ---- pair kernel v2 (reo_pairs2.cu): warp-specialised, symmetric ------------------------------------
+// Row panel and column panel are both [tiles][W][NP][64] with a gene id (and optional sign) per panel position.
+// The first `nsym` row tiles ARE the column panel (same genes, same order): there every unordered pair is
+// evaluated once (tiles I <= J) and updates both genes (src:385-386: q for gene i, 10 - q for gene j).  Row tiles
+// from nsymp = round_up(nsym, T) on are ordinary rows (one-sided update).  nsym == 0: one-sided everywhere.
+struct ReoPair2Params {
+    const uint32_t* row_planes;
+    const uint32_t* col_planes;
+    const int32_t* row_gene;     // [ntr*64] gene of each row position, -1 = pad
+    const int32_t* col_gene;     // [round_up(ntc, 2)*64] gene of each column position, -1 = pad
+    const int8_t* row_sign;      // sign of the row gene AS A COLUMN (symmetric region); nullptr -> +1
+    const int8_t* col_sign;      // [round_up(ntc, 2)*64]; nullptr -> +1
+    int32_t* table;              // [r][9] Int32, this rank's partial sums
+    unsigned int* counter;       // dynamic work counter (zeroed before launch)
+    int ntr, ntc, nsym;          // row tiles, column tiles, symmetric row tiles
+    int T;                       // block edge in tiles (even): one work item = T row tiles x T column tiles
+    int SS;                      // supertile edge in blocks (L2 locality, unit of the rank interleave)
+    int NBs, NBr, NBc;           // blocks: symmetric rows, all rows, columns
+    int Ms, Mc;                  // supertile rows of the symmetric region, supertile columns
+    long long tri, NSUP;         // supertiles in the triangle, supertiles in total
+    int nitems;                  // work items of this rank (its supertiles x SS^2, invalid ones are skipped)
+    int rank, world;
+    int segA0, mixedW, segB0, segB0len, segB1;
+    int W, WA, NP;
+    int nA, nB, padA, padB, thrA, thrB;
+    int mixed;
+    uint32_t maskA, maskB;
+    int KW, NS;                  // sample words per ring stage, ring stages
+    int use_lut, lutSZA, lutSZB;
+    unsigned int one;
+};
+cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st);
+int reo_pairs2_block_edge(int W, int NP);   // T for a staged matrix
+
 // kernels / launchers implemented in the .cu files
 struct ReoDev;  // per-device state (reo_api.cu)
 
@@ -153,5 +187,9 @@ cudaError_t reo_launch_mask_diff(int64_t r, const uint8_t* mask_old, const uint8
                                  int32_t* changed_gene, int8_t* changed_sign, cudaStream_t st);
 // compaction of a mask into an ascending column list (padded to a multiple of 64 with -1); counts[0]=n
 cudaError_t reo_launch_mask_to_list(const uint8_t* mask, int64_t r, int32_t* list, int32_t* count, cudaStream_t st);
+// [C ascending | pad to a T-tile block | N ascending | pad to cap] with signs (see reo_stats.cu)
+cudaError_t reo_launch_sym_lists(int64_t r, const uint8_t* m_old, const uint8_t* m_new, int T, int32_t* gene, int8_t* sign,
+                                 int32_t* counts_out, int64_t cap, cudaStream_t st);
+cudaError_t reo_launch_sum_slices(const int32_t* all, int world, int64_t n, int32_t* out, cudaStream_t st);
 cudaError_t reo_launch_updown(const double* result, int64_t r, double pval_deg, double padj_deg, int8_t* updown,
                               cudaStream_t st);

@@ -33,6 +33,7 @@
 // persistent grid of 3 CTAs per SM; each item accumulates a 9 x 64 table in shared memory and
 // flushes it with integer atomics (order independent, exact).
 #include "reo_internal.cuh"
+#include "reo_ptx.cuh"
 
 #define PK_THREADS 256
 #define PK_WARPS (PK_THREADS / 32)
@@ -73,65 +74,7 @@
 struct PkMeta { int ti, J, w0, nw, flags, pad0, pad1, pad2; };
 struct PkProd { int count, step, nsteps, ti, J, ch, done, jend; };   // producer state (shared memory)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t lop3_b2(uint32_t x, uint32_t y, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xB2;" : "=r"(d) : "r"(x), "r"(y), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t lop3_xor3(uint32_t x, uint32_t y, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(x), "r"(y), "r"(c));
-    return d;
-}
-// acc + pc * k on the FMA pipe (IMAD), keeping the ALU pipe for the LOP3 chains; k derives from a
-// kernel parameter so that ptxas cannot strength-reduce the multiply into ALU shifts/adds
-__device__ __forceinline__ uint32_t mad_acc(uint32_t pc, uint32_t k, uint32_t acc) {
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(pc), "r"(k), "r"(acc));
-    return d;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PK_THREADS) : "memory"); }
-
-// class of one group from a plain count: 0 (i<j stable), 1 (unstable), 2 (i>j stable); src:376-377
-__device__ __forceinline__ uint32_t reo_class(int cnt, int n, int thr) {
-    return (uint32_t)(cnt >= thr) + (uint32_t)(cnt > n - thr);
-}
 
 // NPT > 0: planes known at compile time (fully unrolled chain); NPT == 0: runtime p.NP.
 // LUT: classification through the shared-memory lookup tables (accumulators are shared-memory addresses).

@@ -1,0 +1,74 @@
+// reo_ptx.cuh -- inline-PTX helpers shared by the pair kernels (sm_100a): mbarrier, bulk async copy (UBLKCP),
+// LOP3 with explicit truth tables, shared-memory reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// global -> shared bulk copy (UBLKCP), completion counted in bytes on `bar`; 16-byte aligned addresses and size
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// borrow' = (x & ~y) | (~(x ^ y) & c)
+__device__ __forceinline__ uint32_t lop3_b2(uint32_t x, uint32_t y, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xB2;" : "=r"(d) : "r"(x), "r"(y), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t x, uint32_t y, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(x), "r"(y), "r"(c));
+    return d;
+}
+// acc + pc * k on the FMA pipe (IMAD), keeping the ALU pipe for the LOP3 chains; k derives from a
+// kernel parameter so that ptxas cannot strength-reduce the multiply into ALU shifts/adds
+__device__ __forceinline__ uint32_t mad_acc(uint32_t pc, uint32_t k, uint32_t acc) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(pc), "r"(k), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// class of one group from a plain count: 0 (i<j stable), 1 (unstable), 2 (i>j stable) -- the reference's
+// sequential test, src:376-377:  cnt >= thr ? 3 : (n - cnt >= thr ? 1 : 2)   (1-based there)
+__host__ __device__ __forceinline__ uint32_t reo_class(int cnt, int n, int thr) {
+    return cnt >= thr ? 2u : ((n - cnt) >= thr ? 0u : 1u);
+}

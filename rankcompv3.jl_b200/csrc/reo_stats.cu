@@ -599,7 +599,7 @@ mask_diff_kernel(int64_t r, const uint8_t* __restrict__ mask_old, const uint8_t*
         const uint8_t nd = mask_new[i] != 0, od = mask_old[i] != 0;
         if (od != nd) { changed_gene[pos] = (int32_t)i; changed_sign[pos] = nd ? 1 : -1; ++pos; }
     }
-    const int padded = (t_chg + REO_TILE - 1) / REO_TILE * REO_TILE;
+    const int padded = (t_chg + 2 * REO_TILE - 1) / (2 * REO_TILE) * (2 * REO_TILE);
     for (int i = t_chg + tid; i < padded; i += MK_THREADS) { changed_gene[i] = -1; changed_sign[i] = 0; }
     if (tid == 0) { counts[0] = t_old; counts[1] = t_new; counts[2] = t_chg; }
 }
@@ -625,12 +625,60 @@ mask_to_list_kernel(const uint8_t* __restrict__ mask, int64_t r, int32_t* __rest
     int total;
     int pos = mk_block_scan(n, red, &total);
     for (int64_t i = lo; i < hi; ++i) if (mask[i]) list[pos++] = (int32_t)i;
-    const int padded = (total + REO_TILE - 1) / REO_TILE * REO_TILE;
+    const int padded = (total + 2 * REO_TILE - 1) / (2 * REO_TILE) * (2 * REO_TILE);
     for (int i = total + tid; i < padded; i += MK_THREADS) list[i] = -1;
     if (tid == 0) *count = total;
 }
 cudaError_t reo_launch_mask_to_list(const uint8_t* mask, int64_t r, int32_t* list, int32_t* count, cudaStream_t st) {
     mask_to_list_kernel<<<1, MK_THREADS, 0, st>>>(mask, r, list, count);
+    return cudaGetLastError();
+}
+
+// Lists for the symmetric pair kernel: C = { i : in_c(i) } ascending, pads (-1) up to a whole number of T-tile
+// blocks, then N = the other genes ascending, pads up to `cap`.  in_c(i) = m_new ? (m_old[i] != m_new[i]) : m_old[i];
+// sign = +1 for a gene that enters the reference set (or a plain member), -1 for one that leaves, 0 for N and pads.
+// counts_out[0] = |C|, counts_out[1] = |N|.
+__global__ void __launch_bounds__(MK_THREADS)
+sym_lists_kernel(int64_t r, const uint8_t* __restrict__ m_old, const uint8_t* __restrict__ m_new, int T,
+                 int32_t* __restrict__ gene, int8_t* __restrict__ sign, int32_t* __restrict__ counts_out, int64_t cap) {
+    __shared__ int red[40];
+    const int tid = threadIdx.x;
+    const int64_t per = (r + MK_THREADS - 1) / MK_THREADS;
+    const int64_t lo = (int64_t)tid * per, hi = (lo + per < r) ? lo + per : r;
+    int n_c = 0;
+    for (int64_t i = lo; i < hi; ++i) n_c += m_new ? ((m_old[i] != 0) != (m_new[i] != 0)) : (m_old[i] != 0);
+    const int n_n = (hi > lo ? (int)(hi - lo) : 0) - n_c;
+    int t_c, t_n;
+    int pc = mk_block_scan(n_c, red, &t_c);
+    int pn = mk_block_scan(n_n, red, &t_n);
+    const int64_t blk = (int64_t)T * REO_TILE;
+    const int64_t off_n = (t_c + blk - 1) / blk * blk;
+    for (int64_t i = lo; i < hi; ++i) {
+        const bool od = m_old[i] != 0;
+        const bool in_c = m_new ? (od != (m_new[i] != 0)) : od;
+        if (in_c) { gene[pc] = (int32_t)i; sign[pc] = m_new ? (od ? -1 : 1) : 1; ++pc; }
+        else { gene[off_n + pn] = (int32_t)i; sign[off_n + pn] = 0; ++pn; }
+    }
+    for (int64_t i = t_c + tid; i < off_n; i += MK_THREADS) { gene[i] = -1; sign[i] = 0; }
+    for (int64_t i = off_n + t_n + tid; i < cap; i += MK_THREADS) { gene[i] = -1; sign[i] = 0; }
+    if (tid == 0) { counts_out[0] = t_c; counts_out[1] = t_n; }
+}
+cudaError_t reo_launch_sym_lists(int64_t r, const uint8_t* m_old, const uint8_t* m_new, int T, int32_t* gene, int8_t* sign,
+                                 int32_t* counts_out, int64_t cap, cudaStream_t st) {
+    sym_lists_kernel<<<1, MK_THREADS, 0, st>>>(r, m_old, m_new, T, gene, sign, counts_out, cap);
+    return cudaGetLastError();
+}
+
+// out[i] = sum over q of all[q][i]   (tables of `world` ranks gathered by a user collective)
+__global__ void sum_slices_kernel(const int32_t* __restrict__ all, int world, int64_t n, int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t v = 0;
+    for (int q = 0; q < world; ++q) v += all[(int64_t)q * n + i];
+    out[i] = v;
+}
+cudaError_t reo_launch_sum_slices(const int32_t* all, int world, int64_t n, int32_t* out, cudaStream_t st) {
+    sum_slices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(all, world, n, out);
     return cudaGetLastError();
 }
 
