@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "reo_internal.cuh"
 #include "reo_ptx.cuh"
@@ -54,7 +55,9 @@ struct __align__(128) P2Aux {
     int32_t rgene[64];
     int8_t csgn[128];
     int8_t rsgn[64];
-    int I, J, w0, nw, flags, il, jl, rbase, cbase, pad[7];
+    int flags, nw, kb, w0;       // first 16 bytes: what every stage needs (kb: index in the stage of the first word
+                                 // that is not purely of group A, -1 if none)
+    int I, J, il, jl, rbase, cbase, pad[6];
 };
 static_assert(sizeof(P2Aux) == 1024, "P2Aux must stay 1 KB");
 
@@ -82,10 +85,18 @@ __device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int n, int& b
 }
 
 // NPT > 0: planes known at compile time (fully unrolled chain); NPT == 0: runtime p.NP.
-// LUT: classification through shared-memory lookup tables (accumulators are shared-memory addresses).
-template <int NPT, bool LUT>
+// MODE: how a pair's counts are kept and classified --
+//   P2_WIDE   32-bit counters, compare-based classification (any number of samples);
+//   P2_LUT    classification through shared-memory lookup tables, accumulators ARE table addresses (few samples:
+//             the per-tile epilogue costs loads, not ALU instructions);
+//   P2_PACKED 16-bit counters, two per register, compare-based classification (up to 65535 sample slots per group).
+#define P2_WIDE 0
+#define P2_LUT 1
+#define P2_PACKED 2
+template <int NPT, int MODE>
 __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(const ReoPair2Params p) {
     constexpr int NB = 8;
+    constexpr bool LUT = MODE == P2_LUT, PACKED = MODE == P2_PACKED;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int NP = NPT > 0 ? NPT : p.NP;
     const int KW = p.KW, NS = p.NS, T = p.T;
@@ -179,21 +190,27 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                     const uint32_t* rbase = p.row_planes + (size_t)I * tile_stride;
                     const uint32_t* cbase = p.col_planes + (size_t)Ja * tile_stride;
                     for (int ch = 0; ch < nchunks; ++ch) {
-                        mbar_wait(&empty[slot], ephase);
+                        mbar_wait_parked(&empty[slot], ephase);
                         P2Aux* A = &aux[slot];
                         const int w0 = ch * KW;
                         const int nw = min(KW, p.W - w0);
                         const bool first = ch == 0, last = ch == nchunks - 1;
                         A->I = I; A->J = Ja; A->w0 = w0; A->nw = nw;
+                        A->kb = (p.WA >= w0 && p.WA < w0 + nw) ? p.WA - w0 : -1;
                         A->il = I - I0; A->jl = Ja - J0; A->rbase = I0 * REO_TILE; A->cbase = J0 * REO_TILE;
                         A->flags = tf | (first ? P2F_FIRST_J : 0) | (last ? P2F_LAST_J : 0) |
                                    ((last && left == 0) ? P2F_LAST_ITEM : 0);
                         uint32_t bytes = (uint32_t)nw * op_bytes * (hasB ? 3u : 2u);
-                        if (first) bytes += 256u + 512u + (p.col_sign ? 128u : 0u) + (p.row_sign ? 64u : 0u);
+                        // gene ids travel with the first stage of a tile pair (orientation of the tie coin) and, together
+                        // with the signs, with its last stage (table update): consumers keep none of them in registers
+                        if (first || last) bytes += 256u + 512u;
+                        if (last) bytes += (p.col_sign ? 128u : 0u) + (p.row_sign ? 64u : 0u);
                         mbar_expect_tx(&full[slot], bytes);
-                        if (first) {
+                        if (first || last) {
                             bulk_g2s(A->rgene, p.row_gene + (size_t)I * REO_TILE, 256u, &full[slot]);
                             bulk_g2s(A->cgene, p.col_gene + (size_t)Ja * REO_TILE, 512u, &full[slot]);
+                        }
+                        if (last) {
                             if (p.col_sign) bulk_g2s(A->csgn, p.col_sign + (size_t)Ja * REO_TILE, 128u, &full[slot]);
                             if (p.row_sign) bulk_g2s(A->rsgn, p.row_sign + (size_t)I * REO_TILE, 64u, &full[slot]);
                         }
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
             }
         }
         // no more work: one terminating stage
-        mbar_wait(&empty[slot], ephase);
+        mbar_wait_parked(&empty[slot], ephase);
         aux[slot].flags = P2F_TERM;
         mbar_arrive(&full[slot]);
         return;
@@ -227,57 +244,89 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
     // warp = 8 x 4 threads: 32 rows x (16 + 16) columns; thread = rows ty*4..+3, columns tx*4..+3 of both column tiles
     const int ty = (warp >> 2) * 8 + (lane >> 2);
     const int tx = (warp & 3) * 4 + (lane & 3);
-    uint32_t acc[4][NB];       // 4 * count [+ carried class offset], or lookup-table addresses (LUT)
+    // Accumulators.  WIDE: 4 * count, class of group A carried in bits 28..31.  LUT: shared-memory addresses (see
+    // above).  PACKED: two 16-bit counts per register (column b in the low half, column b + 4 in the high half) and
+    // the classes of group A in two bit fields -- the 16 registers this frees hold the next plane's operands.
+    constexpr int NACC = PACKED ? 4 : NB;
+    uint32_t acc[4][NACC];
+    uint32_t cls_lo = 0u, cls_hi = 0u;   // PACKED: 2 bits per pair (a*4 + b), columns 0..3 / 4..7
     uint32_t om = 0u;          // tie-coin orientation [i<j] of this thread's pairs (all-ones / zero) ...
     uint32_t obits = 0u;       // ... and per pair (bit a*NB+b), used only when the 4 x 8 block is not uniform
     bool uniform = true;       // one orientation, every gene real, no self pair
-    uint32_t csg0 = 0x01010101u, csg1 = 0x01010101u, rsg = 0x01010101u;   // packed int8 signs
-    int curI = 0, curJ = 0;
-    uint32_t rowoff = 0u, coloff = 0u;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[a][b] = 0u;
-    const uint32_t four = p.one << 2;
+        for (int b = 0; b < NACC; ++b) acc[a][b] = 0u;
+    const uint32_t kmul = PACKED ? p.one : (p.one << 2);      // IMAD multipliers (kernel parameters: stay on the FMA pipe)
+    const uint32_t kmul_hi = PACKED ? (p.one << 16) : kmul;
     const uint32_t lut_s = smem_u32(lut);
     const uint32_t tabR_s = smem_u32(tabR), tabC_s = smem_u32(tabC);
 
-    // group-A class of a pair -> new accumulator value (count restarts at 0, class carried along)
-    auto flushA = [&](uint32_t acc4, int idx) -> uint32_t {
-        if (LUT) return lds_u32(acc4);
-        const uint32_t o = (obits >> idx) & 1u;
-        return reo_class((int)(acc4 >> 2) - (int)(o * (uint32_t)p.padA), p.nA, p.thrA) << 28;
+    auto count_of = [&](int a, int b) -> int {   // PACKED / WIDE: plain count of pair (a, b)
+        if (PACKED) return (int)(b < 4 ? (acc[a][b & 3] & 0xffffu) : (acc[a][b & 3] >> 16));
+        return (int)((acc[a][b % NACC] & 0x0fffffffu) >> 2);
+    };
+    // group A finished for every pair: classify ic, restart the counters with the class carried along
+    auto flushA_all = [&]() {
+        if (LUT) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < NACC; ++b) acc[a][b] = lds_u32(acc[a][b]);
+        } else {
+            cls_lo = 0u; cls_hi = 0u;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const uint32_t o = (obits >> (a * NB + b)) & 1u;
+                    const uint32_t cl = reo_class(count_of(a, b) - (int)(o * (uint32_t)p.padA), p.nA, p.thrA);
+                    if (PACKED) { if (b < 4) cls_lo |= cl << (2 * (a * 4 + b)); else cls_hi |= cl << (2 * (a * 4 + (b & 3))); }
+                    else acc[a][b % NACC] = cl << 28;
+                }
+            if (PACKED) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < NACC; ++b) acc[a][b] = 0u;
+            }
+        }
     };
     // (class of A, count of B) -> byte offset of the table bin row
-    auto binB = [&](uint32_t acc4, int idx) -> uint32_t {
-        if (LUT) return lds_u32(acc4);
-        const uint32_t o = (obits >> idx) & 1u;
-        const uint32_t it = reo_class((int)((acc4 & 0x0fffffffu) >> 2) - (int)(o * (uint32_t)p.padB), p.nB, p.thrB);
-        return (3u * (acc4 >> 28) + it) * binstride;
+    auto binB = [&](int a, int b) -> uint32_t {
+        if (LUT) return lds_u32(acc[a][b % NACC]);
+        const uint32_t o = (obits >> (a * NB + b)) & 1u;
+        const uint32_t it = reo_class(count_of(a, b) - (int)(o * (uint32_t)p.padB), p.nB, p.thrB);
+        uint32_t ic;
+        if (PACKED) ic = ((b < 4 ? cls_lo : cls_hi) >> (2 * (a * 4 + (b & 3)))) & 3u;
+        else ic = acc[a][b % NACC] >> 28;
+        return (3u * ic + it) * binstride;
+    };
+    auto add_counts = [&](const uint32_t (&bor)[4][NB], uint32_t mask, bool masked) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const uint32_t pc = (uint32_t)__popc(masked ? (bor[a][b] & mask) : bor[a][b]);
+                acc[a][b % NACC] = mad_acc(pc, (PACKED && b >= 4) ? kmul_hi : kmul, acc[a][b % NACC]);
+            }
     };
 
     int slot = 0;
     uint32_t phase = 0u;
     for (;;) {
-        mbar_wait(&full[slot], phase);
+        mbar_wait_parked(&full[slot], phase);
         const P2Aux* A = &aux[slot];
-        const int flags = A->flags;
+        const int4 hdr = *reinterpret_cast<const int4*>(&A->flags);
+        const int flags = hdr.x;
         if (flags & P2F_TERM) break;
-        const int nw = A->nw, w0 = A->w0;
+        const int nw = hdr.y, kb = hdr.z;
         if (flags & P2F_FIRST_J) {
             const int4 r4 = *reinterpret_cast<const int4*>(A->rgene + ty * 4);
             const int4 c4 = *reinterpret_cast<const int4*>(A->cgene + tx * 4);
             const int4 d4 = *reinterpret_cast<const int4*>(A->cgene + REO_TILE + tx * 4);
             const int gi[4] = {r4.x, r4.y, r4.z, r4.w};
             const int gj[NB] = {c4.x, c4.y, c4.z, c4.w, d4.x, d4.y, d4.z, d4.w};
-            if (p.col_sign) {
-                csg0 = *reinterpret_cast<const uint32_t*>(A->csgn + tx * 4);
-                csg1 = *reinterpret_cast<const uint32_t*>(A->csgn + REO_TILE + tx * 4);
-            }
-            if (p.row_sign) rsg = *reinterpret_cast<const uint32_t*>(A->rsgn + ty * 4);
-            curI = A->I; curJ = A->J;
-            rowoff = (uint32_t)(A->il * REO_TILE + ty * 4) * 4u;
-            coloff = (uint32_t)(A->jl * REO_TILE + tx * 4) * 4u;
             // lists ascend inside a region and pads (-1) come last, so the end points decide
             const bool real = (gi[0] >= 0) && (gi[3] >= 0) && (gj[0] >= 0) && (gj[3] >= 0) && (gj[4] >= 0) && (gj[NB - 1] >= 0);
             const bool all_lt = real && (gi[3] < gj[0]);        // every row gene below every column gene
@@ -298,102 +347,118 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) acc[a][b] = a0;
+                    for (int b = 0; b < NACC; ++b) acc[a][b] = a0;
                 if (!uniform) {
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) acc[a][b] = lut_s + ((obits >> (a * NB + b)) & 1u) * (uint32_t)(SZA * 4);
+                        for (int b = 0; b < NACC; ++b) acc[a][b] = lut_s + ((obits >> (a * NB + b)) & 1u) * (uint32_t)(SZA * 4);
                 }
             } else {
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) acc[a][b] = 0u;
+                    for (int b = 0; b < NACC; ++b) acc[a][b] = 0u;
             }
         }
-        const uint32_t* srow = stages + (size_t)slot * stage_words;
-        const uint32_t* scol = srow + KW * op_words;
-        for (int kk = 0; kk < nw; ++kk) {
-            const bool boundary = (w0 + kk == p.WA);   // first word that is not a pure group-A word
-            if (boundary && !p.mixed) {
-                // group A finished: classify ic, restart the counters with the class carried along
+        // operands of the stage: rows, first column tile, second column tile; this thread's 16-byte chunks.  The
+        // loads run one plane ahead of the LOP3 chain (software pipeline: shared-memory latency never shows).
+        uint32_t xa = smem_u32(stages + (size_t)slot * stage_words) + (uint32_t)ty * 16u;
+        uint32_t ya = smem_u32(stages + (size_t)slot * stage_words + KW * op_words) + (uint32_t)tx * 16u;
+        const uint32_t zoff = (uint32_t)(KW * op_words) * 4u;
+        // word of this stage that is the first not purely of group A (the class of group A is taken there); the
+        // plain words before and after it run in a loop without any test
+        const bool has_b = kb >= 0 && kb < nw;
+        // UNI: one tie-coin orientation for the whole 4 x 8 block (all but the blocks on the diagonal / matrix edges)
+        auto words = [&](auto uni_c) {
+            constexpr bool UNI = decltype(uni_c)::value;
+            uint4 xn = lds_v4(xa), yn = lds_v4(ya), zn = lds_v4(ya + zoff);
+            // borrow chain of one word over all planes; leaves the operands of the next word's plane 0 in xn/yn/zn
+            auto chain = [&](uint32_t (&bor)[4][NB]) {
+                {
+                    const uint32_t x[4] = {xn.x, xn.y, xn.z, xn.w};
+                    const uint32_t y[NB] = {yn.x, yn.y, yn.z, yn.w, zn.x, zn.y, zn.z, zn.w};
+                    xn = lds_v4(xa + 256u); yn = lds_v4(ya + 256u); zn = lds_v4(ya + zoff + 256u);   // plane 1
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < NB; ++b)
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) acc[a][b] = flushA(acc[a][b], a * NB + b);
-            }
-            const uint32_t* xr = srow + kk * op_words + ty * 4;
-            const uint32_t* yc = scol + kk * op_words + tx * 4;
-            const uint32_t* yc2 = yc + KW * op_words;
-            uint32_t bor[4][NB];
-            {
-                const uint4 xv = *reinterpret_cast<const uint4*>(xr);
-                const uint4 yv = *reinterpret_cast<const uint4*>(yc);
-                const uint4 zv = *reinterpret_cast<const uint4*>(yc2);
-                const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                const uint32_t y[NB] = {yv.x, yv.y, yv.z, yv.w, zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) bor[a][b] = lop3_xor3(x[a], y[b], om);
-            }
-            if (!uniform) {   // rare: flip the coin seed of the pairs whose orientation differs from pair (0,0)
-                uint32_t ob = obits;
-                asm volatile("" : "+r"(ob));   // keep the mask arithmetic inside this branch
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) bor[a][b] ^= (0u - (((ob >> (a * NB + b)) ^ ob) & 1u));
-            }
-            if (NPT > 0) {
-#pragma unroll
-                for (int pl = 1; pl < (NPT > 0 ? NPT : 1); ++pl) {
-                    const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
-                    const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
-                    const uint4 zv = *reinterpret_cast<const uint4*>(yc2 + pl * REO_TILE);
-                    const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const uint32_t y[NB] = {yv.x, yv.y, yv.z, yv.w, zv.x, zv.y, zv.z, zv.w};
+                        for (int a = 0; a < 4; ++a) bor[a][b] = lop3_xor3(x[a], y[b], om);
+                }
+                if (!UNI) {   // rare: flip the coin seed of the pairs whose orientation differs from pair (0,0)
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                        for (int b = 0; b < NB; ++b) bor[a][b] ^= (0u - (((obits >> (a * NB + b)) ^ obits) & 1u));
                 }
-            } else {
-#pragma unroll 2
-                for (int pl = 1; pl < NP; ++pl) {
-                    const uint4 xv = *reinterpret_cast<const uint4*>(xr + pl * REO_TILE);
-                    const uint4 yv = *reinterpret_cast<const uint4*>(yc + pl * REO_TILE);
-                    const uint4 zv = *reinterpret_cast<const uint4*>(yc2 + pl * REO_TILE);
-                    const uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const uint32_t y[NB] = {yv.x, yv.y, yv.z, yv.w, zv.x, zv.y, zv.z, zv.w};
+                if (NPT > 0) {
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                    for (int pl = 1; pl < (NPT > 0 ? NPT : 1); ++pl) {
+                        const uint32_t x[4] = {xn.x, xn.y, xn.z, xn.w};
+                        const uint32_t y[NB] = {yn.x, yn.y, yn.z, yn.w, zn.x, zn.y, zn.z, zn.w};
+                        // next plane, or plane 0 of the next word (one word = op_bytes further; past the last word of
+                        // the stage this reads shared memory that is simply not used)
+                        const uint32_t nx = (pl + 1 < NPT) ? (uint32_t)(pl + 1) * 256u : op_bytes;
+                        xn = lds_v4(xa + nx); yn = lds_v4(ya + nx); zn = lds_v4(ya + zoff + nx);
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
-                }
-            }
-            if (boundary && p.mixed) {
-                // the word shared by the tails of both groups: count group A's slots, classify, then
-                // count group B's slots (the masks select real samples only: no pad slots are counted)
+                        for (int b = 0; b < NB; ++b)
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const uint32_t fullA = mad_acc((uint32_t)__popc(bor[a][b] & p.maskA), four, acc[a][b]);
-                        acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b] & p.maskB), four, flushA(fullA, a * NB + b));
+                            for (int a = 0; a < 4; ++a) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
                     }
-            } else {
+                } else {
+#pragma unroll 2
+                    for (int pl = 1; pl < NP; ++pl) {
+                        const uint32_t x[4] = {xn.x, xn.y, xn.z, xn.w};
+                        const uint32_t y[NB] = {yn.x, yn.y, yn.z, yn.w, zn.x, zn.y, zn.z, zn.w};
+                        const uint32_t nx = (pl + 1 < NP) ? (uint32_t)(pl + 1) * 256u : op_bytes;
+                        xn = lds_v4(xa + nx); yn = lds_v4(ya + nx); zn = lds_v4(ya + zoff + nx);
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                        for (int b = 0; b < NB; ++b)
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) acc[a][b] = mad_acc((uint32_t)__popc(bor[a][b]), four, acc[a][b]);
+                            for (int a = 0; a < 4; ++a) bor[a][b] = lop3_b2(x[a], y[b], bor[a][b]);
+                    }
+                }
+                xa += op_bytes; ya += op_bytes;
+            };
+            int done = 0;
+            for (;;) {
+                const int end = (has_b && done <= kb) ? kb : nw;
+                for (; done < end; ++done) {          // plain words
+                    uint32_t bor[4][NB];
+                    chain(bor);
+                    add_counts(bor, 0u, false);
+                }
+                if (done >= nw) break;
+                // the boundary word
+                uint32_t bor[4][NB];
+                if (!p.mixed) {
+                    flushA_all();
+                    chain(bor);
+                    add_counts(bor, 0u, false);
+                } else {
+                    // the word shared by the tails of both groups: count group A's slots, classify, then
+                    // count group B's slots (the masks select real samples only: no pad slots are counted)
+                    chain(bor);
+                    add_counts(bor, p.maskA, true);
+                    flushA_all();
+                    add_counts(bor, p.maskB, true);
+                }
+                ++done;
             }
-        }
+        };
+        if (uniform) words(std::true_type{}); else words(std::false_type{});
         if (flags & P2F_LAST_J) {
             // group B finished: look up the bin; the pair adds sign(j) to bin q of its row gene and, in the symmetric
-            // region, sign(i) to the mirrored bin (8 - q, 0-based; src:385-386) of its column gene
+            // region, sign(i) to the mirrored bin (8 - q, 0-based; src:385-386) of its column gene.  Signs, gene ids
+            // and the tile's place in the block tables come with this (the tile pair's last) stage.
             const uint32_t mirror = 8u * binstride;
+            uint32_t csg0 = 0x01010101u, csg1 = 0x01010101u, rsg = 0x01010101u;   // packed int8 signs
+            if (p.col_sign) {
+                csg0 = *reinterpret_cast<const uint32_t*>(A->csgn + tx * 4);
+                csg1 = *reinterpret_cast<const uint32_t*>(A->csgn + REO_TILE + tx * 4);
+            }
+            if (p.row_sign) rsg = *reinterpret_cast<const uint32_t*>(A->rsgn + ty * 4);
+            const uint32_t rowoff = (uint32_t)(A->il * REO_TILE + ty * 4) * 4u;
+            const uint32_t coloff = (uint32_t)(A->jl * REO_TILE + tx * 4) * 4u;
             if (uniform) {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
@@ -403,25 +468,24 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                     const uint32_t caddr = tabC_s + coloff + (uint32_t)((b >> 2) * REO_TILE * 4 + (b & 3) * 4) + mirror;
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const uint32_t off = binB(acc[a][b], a * NB + b);
+                        const uint32_t off = binB(a, b);
                         if (rowupd) red_shared_add(tabR_s + rowoff + off + (uint32_t)(a * 4), sgc);
                         if (colupd) red_shared_add(caddr - off, (int)(int8_t)(rsg >> (8 * a)));
                     }
                 }
             } else {   // pad genes, self pairs, mixed orientation: matrix edges and the diagonal only
-                int gi[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) gi[a] = p.row_gene[(size_t)curI * REO_TILE + ty * 4 + a];
+                const int4 r4 = *reinterpret_cast<const int4*>(A->rgene + ty * 4);
+                const int gi[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     const bool rowupd = flags & (b < 4 ? P2F_ROW0 : P2F_ROW1);
                     const bool colupd = flags & (b < 4 ? P2F_COL0 : P2F_COL1);
                     const int sgc = (int)(int8_t)((b < 4 ? csg0 : csg1) >> (8 * (b & 3)));
                     const uint32_t caddr = tabC_s + coloff + (uint32_t)((b >> 2) * REO_TILE * 4 + (b & 3) * 4) + mirror;
-                    const int gjb = (rowupd || colupd) ? p.col_gene[(size_t)(curJ + (b >> 2)) * REO_TILE + tx * 4 + (b & 3)] : -1;
+                    const int gjb = A->cgene[(b >> 2) * REO_TILE + tx * 4 + (b & 3)];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const uint32_t off = binB(acc[a][b], a * NB + b);
+                        const uint32_t off = binB(a, b);
                         if (gjb >= 0 && gi[a] >= 0 && gi[a] != gjb) {
                             if (rowupd) red_shared_add(tabR_s + rowoff + off + (uint32_t)(a * 4), sgc);
                             if (colupd) red_shared_add(caddr - off, (int)(int8_t)(rsg >> (8 * a)));
@@ -431,7 +495,8 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
             }
         }
         const bool last_item = flags & P2F_LAST_ITEM;
-        const int rbase = A->rbase, cbase = A->cbase;
+        int rbase = 0, cbase = 0;
+        if (last_item) { rbase = A->rbase; cbase = A->cbase; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);      // this warp is done with the slot (and its header)
         if (last_item) {
@@ -463,25 +528,28 @@ int reo_pairs2_block_edge(int W, int NP) {
     static const int forced = getenv("REO_P2_T") ? atoi(getenv("REO_P2_T")) : 0;
     if (forced == 2 || forced == 4 || forced == 8) return forced;
     const long long work = (long long)W * NP;     // LOP3 per pair
-    if (work >= 512) return 2;
-    if (work >= 64) return 4;
-    return 8;
+    // measured on the 20k x 200 bulk workload (W = 7, 13 planes): T = 2 -> 2.03 ms, 4 -> 2.28 ms, 8 -> 2.94 ms of pair
+    // kernels: small items balance the tail of a launch better than large ones save table flushes
+    return work >= 32 ? 2 : 4;
 }
 
-template <int NPT, bool LUT>
+template <int NPT, int MODE>
 static cudaError_t launch_p2(const ReoPair2Params& p, size_t smem, int num_sms, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(reo_pair2_kernel<NPT, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(reo_pair2_kernel<NPT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int grid = P2_CTAS_PER_SM * num_sms;
     if (grid > p.nitems) grid = p.nitems;
     if (grid < 1) return cudaSuccess;
-    reo_pair2_kernel<NPT, LUT><<<grid, P2_THREADS, smem, st>>>(p);
+    reo_pair2_kernel<NPT, MODE><<<grid, P2_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 template <int NPT>
 static cudaError_t launch_p2_np(const ReoPair2Params& p, size_t smem, int num_sms, cudaStream_t st) {
-    return p.use_lut ? launch_p2<NPT, true>(p, smem, num_sms, st) : launch_p2<NPT, false>(p, smem, num_sms, st);
+    if (p.use_lut) return launch_p2<NPT, P2_LUT>(p, smem, num_sms, st);
+    static const bool no_packed = getenv("REO_P2_NO_PACKED") != nullptr;
+    if (!no_packed && p.nA + p.padA <= 65535 && p.nB + p.padB <= 65535) return launch_p2<NPT, P2_PACKED>(p, smem, num_sms, st);
+    return launch_p2<NPT, P2_WIDE>(p, smem, num_sms, st);
 }
 
 // Fills the geometry (blocks, supertiles, ring) from ntr / ntc / nsym / T / W / NP / rank / world and launches.
@@ -521,7 +589,8 @@ cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st) {
     const size_t avail = (size_t)P2_SMEM_BUDGET - fixed;
     static const int forced_kw = getenv("REO_P2_KW") ? atoi(getenv("REO_P2_KW")) : 0;
     static const int forced_ns = getenv("REO_P2_NS") ? atoi(getenv("REO_P2_NS")) : 0;
-    int KW = (int)std::min<size_t>(3, avail / (4 * (perword + 256)));
+    // long stages amortise the hand-over between stages (measured: 2 stages of 8 words beat 4 of 4)
+    int KW = (int)std::min<size_t>(8, (avail - 2 * sizeof(P2Aux)) / (2 * perword));
     if (forced_kw > 0) KW = forced_kw;
     KW = std::max(1, std::min(KW, p.W));
     {   // spread the words evenly over the steps of one tile pair

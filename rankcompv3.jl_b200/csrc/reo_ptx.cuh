@@ -33,6 +33,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or `ns` nanoseconds
+// pass -- a waiting warp issues (almost) nothing
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait_hint(bar, parity, 1000000u)) { }
+}
 // global -> shared bulk copy (UBLKCP), completion counted in bytes on `bar`; 16-byte aligned addresses and size
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -61,6 +79,11 @@ __device__ __forceinline__ uint32_t mad_acc(uint32_t pc, uint32_t k, uint32_t ac
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
