@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define REO_VERSION 100 /* 0.1.0 */
+#define REO_VERSION 200 /* 0.2.0 */
 
 typedef struct reo_handle_s* reo_handle_t;
 
@@ -62,7 +62,7 @@ typedef enum { REO_I64 = 0, REO_F64 = 1, REO_I32 = 2, REO_F32 = 3 } reo_dtype;
 
 /* Out-struct for logging: lets the Julia shim print the reference's @info lines (src:418-420). */
 typedef struct {
-    int32_t iters_done;                 /* evaluations performed for the last k                     */
+    int32_t iters_done;                 /* evaluations performed for the last k (every k: reo_iter_log) */
     int32_t converged;                  /* 1 if the n_conv criterion stopped the loop (src:419-422) */
     int32_t n_deg[REO_MAX_ITER_LOG];    /* # DEGs per evaluation (src:418)                          */
     int32_t n_ref[REO_MAX_ITER_LOG];    /* size of the reference set used by each evaluation        */
@@ -76,6 +76,9 @@ typedef struct {
     double ms_wall;                     /* whole call, host wall clock                              */
     int32_t pair_launches;              /* pair-kernel launches                                     */
     int32_t kernel_launches;            /* all kernel launches of this call                         */
+    int64_t ordered_triples;            /* (row gene, column gene, sample) triples the evaluated pairs stand
+                                           for: rows x columns x samples per table build (W_ord); `compares`
+                                           counts each mirrored pair once, as the reference does (src:366-372) */
 } reo_stats;
 
 /* Multi-process sharding hook: all-gather `bytes_per_rank` bytes per rank, in place, inside the
@@ -122,6 +125,13 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
                       double pval_deg, double padj_deg, const uint8_t* ref_mask, int32_t n_iter, int32_t n_conv,
                       uint32_t flags, double* result, int8_t* updown, uint8_t* final_ref, int32_t* iters_done,
                       reo_stats* stats);
+
+/* Iteration log of level k (0 <= k < K) of the last reo_identify_degs on this handle: evaluations performed,
+ * whether the n_conv criterion stopped the loop (src:419-422), and per evaluation the number of DEGs (src:418) and
+ * the size of the reference set it used; at most `cap` entries are written.  Lets the Julia shim print the
+ * reference's per-level @info lines (src:418-420, 432-435).  Any output pointer may be NULL. */
+int reo_iter_log(reo_handle_t h, int32_t k, int32_t* iters_done, int32_t* converged, int32_t* n_deg, int32_t* n_ref,
+                 int32_t cap);
 
 /* ---- stage-level entry points (parity tests, benches, profilers) ------------------------- */
 

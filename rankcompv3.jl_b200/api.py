@@ -249,9 +249,19 @@ class Reo:
                      n_ref=list(st.n_ref[:ne]), rank_bits=int(st.rank_bits), sample_words=int(st.sample_words),
                      compares=int(st.compares), ms_stage=st.ms_stage, ms_pairs=st.ms_pairs, ms_stats=st.ms_stats,
                      ms_total=st.ms_total, ms_wall=st.ms_wall, pair_launches=int(st.pair_launches),
-                     kernel_launches=int(st.kernel_launches))
+                     kernel_launches=int(st.kernel_launches), ordered_triples=int(st.ordered_triples))
         # [K, r, 15] view of the library's column-major output (no copy)
         return DegResult(result.transpose(0, 2, 1), updown, final_ref, [int(v) for v in iters], stats)
+
+    def iter_log(self, k: int):
+        """Iteration log of level k of the last identify_degs: dict(iters_done, converged, n_deg[], n_ref[]) -- what the
+        reference prints per level (src:418-420, 432-435)."""
+        it, cv = C.c_int32(), C.c_int32()
+        nd = np.zeros(L.REO_MAX_ITER_LOG, dtype=np.int32)
+        nr = np.zeros(L.REO_MAX_ITER_LOG, dtype=np.int32)
+        self._check(self._lib.reo_iter_log(self._h, int(k), C.byref(it), C.byref(cv), _ptr(nd), _ptr(nr), len(nd)))
+        n = min(it.value, len(nd))
+        return dict(iters_done=it.value, converged=cv.value, n_deg=nd[:n].tolist(), n_ref=nr[:n].tolist())
 
     # -- stage-level entry points -----------------------------------------------------------------
     def stage(self, data, group_id, gnum):

@@ -10,7 +10,10 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <thread>
 #include <mutex>
 #include <new>
@@ -75,6 +78,60 @@ std::mutex g_nccl_mu;
 
 }  // namespace
 
+// A few host threads that copy slices of a pageable input matrix into pinned bounce buffers (one memcpy thread
+// cannot keep up with PCIe; see do_stage).
+class CopyPool {
+public:
+    explicit CopyPool(int n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return (int)th_.size(); }
+    // runs f(part, nparts) on every thread and returns when all are done
+    void run(const std::function<void(int, int)>& f) {
+        std::unique_lock<std::mutex> g(mu_);
+        job_ = &f; pending_ = (int)th_.size(); ++gen_;
+        cv_.notify_all();
+        done_.wait(g, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+private:
+    void loop(int i) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)>* f;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_; f = job_;
+            }
+            (*f)(i, (int)th_.size());
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)>* job_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+struct LevelLog {   // what the reference prints per level k (src:418-420, 432-435)
+    int32_t iters_done = 0, converged = 0;
+    std::vector<int32_t> n_deg, n_ref;
+};
+
+#define REO_NBOUNCE 4
 struct ReoDev {
     int dev = 0;
     int num_sms = 148;
@@ -100,6 +157,10 @@ struct ReoDev {
     int32_t* h_counts = nullptr;  // pinned
     uint8_t* h_out = nullptr;     // pinned staging for results (grow-only)
     size_t h_out_cap = 0;
+    uint8_t* bounce[REO_NBOUNCE] = {};   // pinned bounce buffers for pageable input (lazily allocated)
+    size_t bounce_cap = 0;
+    cudaEvent_t bounce_ev[REO_NBOUNCE] = {};
+    CopyPool* pool = nullptr;
     bool early_pending = false;   // a copy of result columns 2..14 is in flight on st_copy (ev[7] marks its end)
     int32_t* table_cur = nullptr; // tables the statistics read: `table` (one rank) or `table_red` (sum over ranks)
     int64_t list_cap = 0;         // entries of the gene lists (col_gene, changed_*, list_*, iota)
@@ -126,6 +187,8 @@ struct reo_handle_s {
     int64_t compares = 0;
     // single-process multi-GPU: one rank handle per device, driven by one host thread each
     std::vector<reo_handle_s*> subs;
+    std::vector<LevelLog> logs;   // per level k of the last reo_identify_degs
+    int64_t ordered_triples = 0;  // rows x columns x samples the evaluated pairs stand for (W_ord of SURVEY 8d)
 };
 
 namespace {
@@ -364,6 +427,32 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         chunk = std::max<int64_t>(D.num_sms, chunk / D.num_sms * D.num_sms);
     }
     chunk = std::max<int64_t>(chunk, 1);
+    bool pageable = false;
+    if (!on_dev) {
+        cudaPointerAttributes pa;
+        const cudaError_t pe = cudaPointerGetAttributes(&pa, data);
+        if (pe != cudaSuccess) { cudaGetLastError(); pageable = true; }
+        else pageable = (pa.type == cudaMemoryTypeUnregistered);
+        static const bool no_bounce = getenv("REO_NO_BOUNCE") != nullptr;
+        if (no_bounce) pageable = false;
+    }
+    if (pageable) {
+        const size_t need = (size_t)chunk * r * es;
+        if (need > D.bounce_cap) {
+            for (auto& bptr : D.bounce) { if (bptr) cudaFreeHost(bptr); bptr = nullptr; }
+            D.bounce_cap = 0;
+            for (auto& bptr : D.bounce) CK(cudaMallocHost((void**)&bptr, need));
+            D.bounce_cap = need;
+        }
+        for (auto& e : D.bounce_ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (!D.pool) {
+            int nt = 8;
+            if (const char* e = getenv("REO_COPY_THREADS")) nt = atoi(e);
+            const int hc = (int)std::thread::hardware_concurrency();
+            if (hc > 0) nt = std::min(nt, std::max(1, hc / std::max(1, h->world)));
+            D.pool = new CopyPool(std::max(1, nt));
+        }
+    }
     if (!on_dev) {   // the copy stream must not overtake work still queued on `st` that reads/frees `raw`
         CK(cudaEventRecord(D.ev[5], D.st));
         CK(cudaStreamWaitEvent(D.st_copy, D.ev[5], 0));
@@ -375,9 +464,25 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         while (j0 + n < nmy && n < chunk && my_samples[j0 + n] == my_samples[j0] + n) ++n;
         if (!on_dev) {
             // copy on the copy stream, rank on the compute stream as soon as this chunk has landed
-            CK(cudaMemcpy2DAsync(D.raw.p + (size_t)j0 * r * es, (size_t)r * es,
-                                 (const uint8_t*)data + (size_t)my_samples[j0] * ld * es, (size_t)ld * es, (size_t)r * es,
-                                 (size_t)n, cudaMemcpyHostToDevice, D.st_copy));
+            const uint8_t* src = (const uint8_t*)data + (size_t)my_samples[j0] * ld * es;
+            if (pageable) {
+                // pageable input (a Julia Matrix): a few host threads fill a pinned bounce buffer while the DMA engine
+                // drains the previous ones -- the driver's own pageable path is several times slower than PCIe
+                const int b = (int)(n_chunk % REO_NBOUNCE);
+                if (n_chunk >= REO_NBOUNCE) CK(cudaEventSynchronize(D.bounce_ev[b]));
+                uint8_t* dstb = D.bounce[b];
+                const size_t colb = (size_t)r * es, ldb = (size_t)ld * es;
+                D.pool->run([&](int part, int nparts) {
+                    const int64_t c0 = n * part / nparts, c1 = n * (part + 1) / nparts;
+                    if (ldb == colb) { if (c1 > c0) memcpy(dstb + c0 * colb, src + c0 * colb, (size_t)(c1 - c0) * colb); }
+                    else for (int64_t q = c0; q < c1; ++q) memcpy(dstb + q * colb, src + q * ldb, colb);
+                });
+                CK(cudaMemcpyAsync(D.raw.p + (size_t)j0 * r * es, dstb, (size_t)n * colb, cudaMemcpyHostToDevice, D.st_copy));
+                CK(cudaEventRecord(D.bounce_ev[b], D.st_copy));
+            } else {
+                CK(cudaMemcpy2DAsync(D.raw.p + (size_t)j0 * r * es, (size_t)r * es, src, (size_t)ld * es, (size_t)r * es,
+                                     (size_t)n, cudaMemcpyHostToDevice, D.st_copy));
+            }
             if (n_chunk >= D.copy_ev.size()) {
                 cudaEvent_t ev;
                 CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -579,6 +684,7 @@ int launch_tables_v1(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_
     if ((rc = record_pair_events(h, D, false))) return rc;
     const int64_t rows = std::min<int64_t>(S.r, (int64_t)p.t1 * REO_TILE) - (int64_t)p.t0 * REO_TILE;
     h->compares += std::max<int64_t>(rows, 0) * (int64_t)ncols * S.c;
+    h->ordered_triples += std::max<int64_t>(rows, 0) * (int64_t)ncols * S.c;
     return REO_OK;
 }
 
@@ -651,6 +757,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* 
     CKL(reo_launch_pairs2(p, D.num_sms, D.st));
     if ((rc = record_pair_events(h, D, false))) return rc;
     h->compares += rank_share(h, executed);
+    h->ordered_triples += rank_share(h, rr * nc * S.c);
     return REO_OK;
 }
 
@@ -912,6 +1019,9 @@ int reo_destroy(reo_handle_t h) {
         if (D.sortws.cnt) cudaFree(D.sortws.cnt);
         if (D.h_counts) cudaFreeHost(D.h_counts);
         if (D.h_out) cudaFreeHost(D.h_out);
+        for (auto& bptr : D.bounce) if (bptr) cudaFreeHost(bptr);
+        for (auto& e : D.bounce_ev) if (e) cudaEventDestroy(e);
+        delete D.pool; D.pool = nullptr;
         D.std_ws.release();
         for (auto& ev : D.ev) if (ev) cudaEventDestroy(ev);
         for (auto& ev : D.pev) cudaEventDestroy(ev);
@@ -955,7 +1065,7 @@ int reo_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c,
         if (flags & REO_DATA_ON_DEVICE) return fail(h, REO_ERR_UNSUPPORTED, "REO_DATA_ON_DEVICE needs a single-device handle");
         return run_multi(h, [&](reo_handle_t s, int) { return reo_stage(s, data, dtype, r, c, ld, group_id, gnum, flags); });
     }
-    h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0;
+    h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0; h->ordered_triples = 0;
     h->devs[0].n_pev = 0;
     return do_stage(h, data, dtype, r, c, ld, group_id, gnum, flags);
 }
@@ -1200,6 +1310,20 @@ int reo_subset(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c
     return REO_OK;
 }
 
+/* Per-level iteration log of the last reo_identify_degs (the reference's @info lines, src:418-420, 432-435). */
+int reo_iter_log(reo_handle_t h, int32_t k, int32_t* iters_done, int32_t* converged, int32_t* n_deg, int32_t* n_ref,
+                 int32_t cap) {
+    if (!h) return REO_ERR_ARG;
+    if (!h->subs.empty()) { const int rc = reo_iter_log(h->subs[0], k, iters_done, converged, n_deg, n_ref, cap); if (rc) h->err = h->subs[0]->err; return rc; }
+    if (k < 0 || k >= (int)h->logs.size()) return fail(h, REO_ERR_ARG, "reo_iter_log: no such level in the last reo_identify_degs");
+    const LevelLog& L = h->logs[k];
+    if (iters_done) *iters_done = L.iters_done;
+    if (converged) *converged = L.converged;
+    const int n = std::min<int>(cap, (int)L.n_deg.size());
+    for (int i = 0; i < n; ++i) { if (n_deg) n_deg[i] = L.n_deg[i]; if (n_ref) n_ref[i] = L.n_ref[i]; }
+    return REO_OK;
+}
+
 int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, int64_t ld,
                       const int32_t* group_id, int32_t gnum, const int32_t* thresholds, double pval_reo,
                       double pval_deg, double padj_deg, const uint8_t* ref_mask, int32_t n_iter, int32_t n_conv,
@@ -1225,7 +1349,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         if (rc == REO_OK && stats) {
             *stats = sts[0];
             for (size_t i = 1; i < n; ++i) {  // whole-job work; times are the slowest rank's
-                stats->compares += sts[i].compares;
+                stats->compares += sts[i].compares; stats->ordered_triples += sts[i].ordered_triples;
                 stats->kernel_launches += sts[i].kernel_launches; stats->pair_launches += sts[i].pair_launches;
                 stats->ms_total = std::max(stats->ms_total, sts[i].ms_total);
                 stats->ms_pairs = std::max(stats->ms_pairs, sts[i].ms_pairs);
@@ -1241,7 +1365,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     ReoDev& D = h->devs[0];
     const auto wall0 = std::chrono::steady_clock::now();
     CK(cudaSetDevice(D.dev));
-    h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0;
+    h->kernel_launches = 0; h->pair_launches = 0; h->compares = 0; h->ordered_triples = 0;
     cudaEvent_t e_start = D.ev[0], e_staged = D.ev[1], e_end = D.ev[2];
     D.n_pev = 0;
     CK(cudaEventRecord(e_start, D.st));
@@ -1272,6 +1396,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         ~CopyGuard() { if (D.early_pending) { cudaStreamSynchronize(D.st_copy); D.early_pending = false; } }
     } copy_guard{D};
 
+    h->logs.assign(K, LevelLog());
     for (int k = 0; k < K; ++k) {
         LevelPlan P = make_plan(S, k, thresholds, pval_reo);
         if ((rc = upload_plan(h, D, P))) return rc;
@@ -1301,6 +1426,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
             CK(cudaStreamSynchronize(D.st));
             const int n_ref = D.h_counts[0], n_inds = D.h_counts[1], n_chg = D.h_counts[2];
             if (n_eval < REO_MAX_ITER_LOG) { st_local.n_deg[n_eval] = (int32_t)r - n_inds; st_local.n_ref[n_eval] = n_ref; }
+            h->logs[k].n_deg.push_back((int32_t)r - n_inds); h->logs[k].n_ref.push_back(n_ref);
             n_eval++;
             if (abs(n_ref - n_inds) < n_conv) {  // src:419-422
                 converged = 1;
@@ -1331,6 +1457,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         if (D.early_pending) { CK(cudaStreamSynchronize(D.st_copy)); D.early_pending = false; }
         it_host[k] = n_eval;
         st_local.iters_done = n_eval; st_local.converged = converged;
+        h->logs[k].iters_done = n_eval; h->logs[k].converged = converged;
     }
     const auto wall2 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(e_end, D.st));
@@ -1352,6 +1479,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     if (iters_done) memcpy(iters_done, it_host.data(), K * sizeof(int32_t));
     if (stats) {
         st_local.rank_bits = S.B; st_local.sample_words = S.W; st_local.compares = h->compares;
+        st_local.ordered_triples = h->ordered_triples;
         st_local.ms_stage = ms_stage; st_local.ms_pairs = ms_pairs; st_local.ms_total = ms_total;
         st_local.ms_stats = ms_total - ms_stage - ms_pairs;
         st_local.pair_launches = h->pair_launches; st_local.kernel_launches = h->kernel_launches;

@@ -355,6 +355,18 @@ def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
             os.environ.pop("REO_K1_SHARD_MIN", None)
 
 
+# ---- one process per GPU (the torchrun deployment shape): NCCL inside the library ------------------------
+def test_one_process_per_gpu_matches_oracle(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import mp_worker
+    mp.spawn(mp_worker.run, args=(world, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok_{q}")) for q in range(world))
+
+
 # ---- next to the path: pseudo-bulk, detection filters, subsetting ---------------
 @pytest.mark.parametrize("dtype", [np.int64, np.int32, np.float64, np.float32])
 def test_pseudobulk_detect_subset(reo, pkg, dtype):
