@@ -93,11 +93,13 @@ struct ReoPair2Params {
     unsigned int* counter;       // dynamic work counter (zeroed before launch)
     int ntr, ntc, nsym;          // row tiles, column tiles, symmetric row tiles
     int T;                       // block edge in tiles (even): one work item = T row tiles x T column tiles
-    int SS;                      // supertile edge in blocks (L2 locality, unit of the rank interleave)
+    int SS;                      // supertile edge in blocks (L2 locality)
+    int perm_mul;                // unit modulo SS*SS*RS that scrambles the item order inside a supertile
+    int RS;                      // row parts per block: one work item = T / RS row tiles x T column tiles
     int NBs, NBr, NBc;           // blocks: symmetric rows, all rows, columns
     int Ms, Mc;                  // supertile rows of the symmetric region, supertile columns
     long long tri, NSUP;         // supertiles in the triangle, supertiles in total
-    int nitems;                  // work items of this rank (its supertiles x SS^2, invalid ones are skipped)
+    int nitems;                  // work items of this rank (every world-th item; invalid ones are skipped)
     int rank, world;
     int segA0, mixedW, segB0, segB0len, segB1;
     int W, WA, NP;

@@ -63,12 +63,19 @@ static_assert(sizeof(P2Aux) == 1024, "P2Aux must stay 1 KB");
 
 __device__ __forceinline__ void p2_consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(P2_CONSUMERS) : "memory"); }
 
-// work item n of this rank -> block (bi, bj); false: nothing to do for this index
-__device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int n, int& bi, int& bj) {
-    const int ss2 = p.SS * p.SS;
-    const int k = n / ss2, li = n - k * ss2;
-    const long long s = (long long)k * p.world + p.rank;
+// work item n of this rank -> block (bi, bj) and row part `sub` of the block; false: nothing to do for this index.
+// Items are numbered supertile by supertile (L2 locality of the CTAs in flight) and dealt round-robin to the ranks:
+// every rank gets the same number of items of every supertile (+-1), whatever the shape of the tile space.
+__device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int n, int& bi, int& bj, int& sub) {
+    const long long g = (long long)n * p.world + p.rank;
+    const int per_sup = p.SS * p.SS * p.RS;
+    const long long s = g / per_sup;
     if (s >= p.NSUP) return false;
+    // inside a supertile the items are visited in a scrambled order (multiplication by a unit modulo their number):
+    // the valid items of a diagonal supertile then spread evenly over the ranks
+    const int li0 = (int)(((g - s * per_sup) * p.perm_mul + s) % per_sup);
+    const int li = li0 / p.RS;
+    sub = li0 - li * p.RS;
     const int di = li / p.SS, dj = li - di * p.SS;
     if (s < p.tri) {   // symmetric region: supertile row SI holds supertile columns SI .. Ms-1
         int si = 0;
@@ -158,11 +165,13 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
         for (;;) {
             const int n = (int)atomicAdd(p.counter, 1u);
             if (n >= p.nitems) break;
-            int bi, bj;
-            if (!p2_decode(p, n, bi, bj)) continue;
+            int bi, bj, sub;
+            if (!p2_decode(p, n, bi, bj, sub)) continue;
             const bool symrow = bi < p.NBs;
-            const int I0 = bi * T, J0 = bj * T;
-            const int Iend = symrow ? min(I0 + T, p.nsym) : min(I0 + T, p.ntr);
+            const int TI = T / p.RS;                       // row tiles of one item
+            const int B0 = bi * T, J0 = bj * T;            // first row / column tile of the block
+            const int I0 = B0 + sub * TI;
+            const int Iend = symrow ? min(I0 + TI, p.nsym) : min(I0 + TI, p.ntr);
             const int Jend = min(J0 + T, p.ntc);
             const int jphi = (Jend + 1) >> 1;
             int left = 0;            // tile pairs (64 x 128) of this item
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                         const bool first = ch == 0, last = ch == nchunks - 1;
                         A->I = I; A->J = Ja; A->w0 = w0; A->nw = nw;
                         A->kb = (p.WA >= w0 && p.WA < w0 + nw) ? p.WA - w0 : -1;
-                        A->il = I - I0; A->jl = Ja - J0; A->rbase = I0 * REO_TILE; A->cbase = J0 * REO_TILE;
+                        A->il = I - B0; A->jl = Ja - J0; A->rbase = B0 * REO_TILE; A->cbase = J0 * REO_TILE;
                         A->flags = tf | (first ? P2F_FIRST_J : 0) | (last ? P2F_LAST_J : 0) |
                                    ((last && left == 0) ? P2F_LAST_ITEM : 0);
                         uint32_t bytes = (uint32_t)nw * op_bytes * (hasB ? 3u : 2u);
@@ -560,10 +569,9 @@ cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st) {
     const int nsymp = p.NBs * T;
     p.NBr = p.nsym > 0 ? p.NBs + (std::max(p.ntr - nsymp, 0) + T - 1) / T : (p.ntr + T - 1) / T;
     p.NBc = (p.ntc + T - 1) / T;
-    // supertile edge: ~24 tiles (both operand sets of the CTAs in flight stay in L2); smaller when several ranks share
-    // the supertiles round-robin, and never so large that a rank is left with only a handful of them
+    // supertile edge: ~24 tiles (both operand sets of the CTAs in flight stay in L2)
     static const int forced_ss = getenv("REO_P2_SS") ? atoi(getenv("REO_P2_SS")) : 0;
-    int SS = std::max(1, (p.world > 1 ? 12 : 24) / T);
+    int SS = std::max(1, 24 / T);
     if (forced_ss > 0) SS = forced_ss;
     for (;;) {
         p.SS = SS;
@@ -572,11 +580,23 @@ cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st) {
         const int Mr = (p.NBr - p.NBs + SS - 1) / SS;
         p.tri = (long long)p.Ms * (p.Ms + 1) / 2;
         p.NSUP = p.tri + (long long)Mr * p.Mc;
-        if (SS == 1 || forced_ss > 0 || p.NSUP >= 48LL * p.world) break;
+        if (SS == 1 || forced_ss > 0 || p.NSUP >= 8) break;
         SS = SS > 2 ? SS / 2 : 1;
     }
-    const long long mine = p.NSUP > p.rank ? (p.NSUP - p.rank + p.world - 1) / p.world : 0;
-    p.nitems = (int)std::min<long long>(mine * p.SS * p.SS, 0x7fffffff);
+    // long tile pairs (thousands of sample words): one row tile per item, so that the tail of a launch stays short
+    static const int forced_rs = getenv("REO_P2_RS") ? atoi(getenv("REO_P2_RS")) : 0;
+    p.RS = ((long long)p.W * p.NP >= 1024) ? T : 1;
+    if (forced_rs > 0 && T % forced_rs == 0) p.RS = forced_rs;
+    {
+        const int per_sup = p.SS * p.SS * p.RS;
+        int m = 7;
+        while (std::__gcd(m, per_sup) != 1) m += 2;
+        p.perm_mul = per_sup > 1 ? m % per_sup : 1;
+        if (p.perm_mul == 0) p.perm_mul = 1;
+    }
+    const long long total_items = p.NSUP * p.SS * p.SS * p.RS;
+    const long long mine = total_items > p.rank ? (total_items - p.rank + p.world - 1) / p.world : 0;
+    p.nitems = (int)std::min<long long>(mine, 0x7fffffff);
     if (p.nitems <= 0) return cudaSuccess;
     // lookup tables
     const int sza = p.nA + p.padA + 1, szb = p.nB + p.padB + 1;
