@@ -32,6 +32,8 @@ def lib():
         L.reo_oracle_num_threads.restype = C.c_int
         L.reo_oracle_set_threads.restype = None
         L.reo_oracle_set_threads.argtypes = [C.c_int]
+        L.reo_oracle_set_coin_mode.restype = None
+        L.reo_oracle_set_coin_mode.argtypes = [C.c_int]
         L.reo_oracle_threshold.restype = C.c_int
         L.reo_oracle_threshold.argtypes = [C.c_int, C.c_double]
         L.reo_oracle_mccullagh.restype = None
@@ -81,6 +83,11 @@ def use_all_cores() -> int:
         n = os.cpu_count() or 1
     lib().reo_oracle_set_threads(int(n))
     return num_threads()
+
+
+def set_coin_mode(mode: int) -> None:
+    """0: the product's XOR coin rule; 1: independent per-pair coins (study of the tie rule only, scripts/coin_study.py)."""
+    lib().reo_oracle_set_coin_mode(int(mode))
 
 
 def threshold(n: int, pval: float) -> int:

@@ -194,7 +194,22 @@ typedef struct {
     const double* xt;   /* gene-major copy: xt[i*c + s] */
     const uint8_t* ut;  /* coins, same layout */
     const int32_t* gid; /* level of each sample */
+    uint64_t seed;
+    const int32_t* gidx; /* global gene index of local row i (NULL: identity) */
 } reo_ctx;
+
+/* Tie-coin variants (study only; the product and every parity test use mode 0):
+ *   0  coin(i,j,s) = u(i,s) ^ u(j,s) ^ [i<j]          -- G bits of entropy per sample, free in the bit-sliced kernel
+ *   1  coin(i,j,s) = h(seed, min(i,j), max(i,j), s)    -- an independent fair coin per (unordered pair, sample), which is
+ *                     what the reference's rand(Bool) (src:73) draws; mirrored for (j,i) as src:385-386 requires */
+static int g_coin_mode = 0;
+void reo_oracle_set_coin_mode(int mode) { g_coin_mode = mode; }
+static inline uint32_t pair_coin(uint64_t seed, uint32_t lo, uint32_t hi, uint32_t s) {
+    uint32_t h = mix32(((uint32_t)seed) ^ (lo * 0x9E3779B1u));
+    h = mix32(h + hi * 0x85EBCA77u + (uint32_t)(seed >> 32));
+    h = mix32(h ^ (s * 0xC2B2AE35u));
+    return h >> 31;
+}
 
 /* nre[g] for g < gnum: count of samples of level g where gene i "is greater" than gene j */
 static inline void pair_counts(const reo_ctx* x, int64_t i, int64_t j, int64_t* nre) {
@@ -207,7 +222,14 @@ static inline void pair_counts(const reo_ctx* x, int64_t i, int64_t j, int64_t* 
     for (int64_t s = 0; s < x->c; ++s) {
         double d = a[s] - b[s];
         int gt;
-        if (fabs(d) < 0.1) gt = ua[s] ^ ub[s] ^ o;  /* src:72-73, deterministic coin */
+        if (fabs(d) < 0.1) {                         /* src:72-73, deterministic coin */
+            if (g_coin_mode == 0) gt = ua[s] ^ ub[s] ^ o;
+            else {
+                const uint32_t gi = (uint32_t)(x->gidx ? x->gidx[i] : i), gj = (uint32_t)(x->gidx ? x->gidx[j] : j);
+                const uint32_t cbit = pair_coin(x->seed, gi < gj ? gi : gj, gi < gj ? gj : gi, (uint32_t)s);
+                gt = (int)(o ? cbit : (cbit ^ 1u));
+            }
+        }
         else gt = a[s] > b[s];                       /* src:75 */
         nre[x->gid[s]] += gt;
     }
@@ -228,7 +250,7 @@ static void make_ctx_idx(reo_ctx* x, const double* data, int64_t r, int64_t c, i
             xt[i * c + s] = data[i + ld * s];
             ut[i * c + s] = (uint8_t)reo_oracle_u(seed, (uint32_t)(gidx ? gidx[i] : i), (uint32_t)s);
         }
-    x->r = r; x->c = c; x->gnum = gnum; x->xt = xt; x->ut = ut; x->gid = gid;
+    x->r = r; x->c = c; x->gnum = gnum; x->xt = xt; x->ut = ut; x->gid = gid; x->seed = seed; x->gidx = gidx;
     *xt_out = xt; *ut_out = ut;
 }
 
@@ -242,7 +264,7 @@ static void make_ctx(reo_ctx* x, const double* data, int64_t r, int64_t c, int64
             xt[i * c + s] = data[i + ld * s];
             ut[i * c + s] = (uint8_t)reo_oracle_u(seed, (uint32_t)i, (uint32_t)s);
         }
-    x->r = r; x->c = c; x->gnum = gnum; x->xt = xt; x->ut = ut; x->gid = gid;
+    x->r = r; x->c = c; x->gnum = gnum; x->xt = xt; x->ut = ut; x->gid = gid; x->seed = seed; x->gidx = NULL;
     *xt_out = xt; *ut_out = ut;
 }
 

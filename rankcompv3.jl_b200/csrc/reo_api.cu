@@ -1470,6 +1470,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
         float ms = 0;
         cudaEventElapsedTime(&ms, D.pev[2 * i], D.pev[2 * i + 1]);
         ms_pairs += ms;
+        if (getenv("REO_TIMING")) fprintf(stderr, "[reo timing] rank %d pair launch %d: %.3f ms\n", h->rank, i, (double)ms);
     }
     if (!direct) {
         memcpy(result, res_host, res_bytes);

@@ -355,6 +355,22 @@ def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
             os.environ.pop("REO_K1_SHARD_MIN", None)
 
 
+# ---- the UNMODIFIED reference's own outputs (tie-free inputs), when a maintainer with Julia has dumped them -------
+def test_reference_julia_fixtures(reo, oracle):
+    """tests/golden/julia_out/<case>.tsv = RankCompV3.identify_degs run by julia/dump_reference_fixture.jl on the inputs
+    of scripts/make_tiefree_inputs.py.  There is no Julia in the build image: missing fixtures are reported as xfail."""
+    import julia_fixtures as jf
+    have = [c for c in jf.cases() if jf.load_reference_output(c) is not None]
+    if not have:
+        pytest.xfail("reference fixtures missing: run julia/dump_reference_fixture.jl where Julia is available")
+    for case in have:
+        genes, data, group, ref, (pval_reo, pval_deg, padj_deg, n_iter, n_conv) = jf.load_input(case)
+        levels, gid = oracle.group_levels(group)
+        out = reo.identify_degs(data, gid, len(levels), ref, pval_reo, pval_deg, padj_deg, n_iter, n_conv)
+        want_result, want_updown = jf.load_reference_output(case)
+        jf.compare(out.result, out.updown, want_result, want_updown)
+
+
 # ---- one process per GPU (the torchrun deployment shape): NCCL inside the library ------------------------
 def test_one_process_per_gpu_matches_oracle(tmp_path):
     import torch

@@ -190,3 +190,25 @@ def test_tie_coins_are_fair_and_mirrored(oracle):
     obs = np.histogram(w01, bins=edges)[0]
     exp = np.diff(binom.cdf(np.array(edges) - 1, T, 0.5)) * len(w01)
     assert ((obs - exp) ** 2 / exp).sum() < 40
+
+
+def test_oracle_against_reference_julia_fixtures(oracle, coracle):
+    """Pins BOTH restatements on the unmodified reference when its outputs are present (see tests/julia_fixtures.py); on
+    the tie-free inputs the oracle must in any case be independent of the tie seed."""
+    import julia_fixtures as jf
+    missing = []
+    for case in jf.cases():
+        genes, data, group, ref, (pval_reo, pval_deg, padj_deg, n_iter, n_conv) = jf.load_input(case)
+        levels, gid = oracle.group_levels(group)
+        gnum = len(levels)
+        thr = coracle.thresholds_for(gid, gnum, pval_reo)
+        a = coracle.identify_degs(data, gid, gnum, thr, pval_deg, padj_deg, ref, n_iter, n_conv, seed=7)
+        b = coracle.identify_degs(data, gid, gnum, thr, pval_deg, padj_deg, ref, n_iter, n_conv, seed=12345)
+        assert np.array_equal(a["result"], b["result"]) and np.array_equal(a["updown"], b["updown"])   # no tie, no coin
+        want = jf.load_reference_output(case)
+        if want is None:
+            missing.append(case)
+            continue
+        jf.compare(a["result"], a["updown"], want[0], want[1])
+    if missing:
+        pytest.xfail("reference fixtures missing for " + ", ".join(missing) + ": run julia/dump_reference_fixture.jl")
