@@ -380,14 +380,15 @@ def nccl_unique_id() -> bytes:
 
 
 # ---- module-level default handle ------------------------------------------------------------------
-_default = None
+_default: dict = {}
 
 
 def default_handle(seed: int = 0) -> Reo:
-    global _default
-    if _default is None:
-        _default = Reo(int(os.environ.get("LOCAL_RANK", "0")), seed)
-    return _default
+    """One cached handle per (device, tie seed): a second call with another seed gets its own coins."""
+    key = (int(os.environ.get("LOCAL_RANK", "0")), int(seed))
+    if key not in _default:
+        _default[key] = Reo(key[0], key[1])
+    return _default[key]
 
 
 # ---- reference-named functions ----------------------------------------------------------------------

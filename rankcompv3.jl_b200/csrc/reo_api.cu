@@ -314,6 +314,9 @@ int ensure_h_out(reo_handle_t h, ReoDev& D, size_t bytes) {
 }
 
 int upload_plan(reo_handle_t h, ReoDev& D, const LevelPlan& P) {
+    // src:85: findfirst(pval .> pval_reo) returns nothing when no count can reach significance -- the reference throws there
+    if (P.thrA < 0 || P.thrB < 0)
+        return fail(h, REO_ERR_ARG, "no stable-REO threshold for this pval_reo (src:85 finds no count): pval_reo must be below 1");
     CK(D.word_order.ensure(P.word_order.size()));
     CK(cudaMemcpyAsync(D.word_order.p, P.word_order.data(), P.word_order.size() * 4, cudaMemcpyHostToDevice, D.st));
     return REO_OK;

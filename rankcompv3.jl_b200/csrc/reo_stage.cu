@@ -13,6 +13,8 @@
 // All are HBM/L2-bound streaming passes; algorithmic bytes are stated in DESIGN.md.
 #include <limits.h>
 
+#include <algorithm>
+
 #include "reo_internal.cuh"
 
 #define RK_THREADS 1024                 // both tiers and the fallback
@@ -326,9 +328,11 @@ bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
     __shared__ uint32_t tile[128 * LD];                 // [slot][gene]
     __shared__ uint32_t ghash[REO_TILE];                // inner hash of the coin, per gene
     __shared__ int so_s[128];
-    const int t = blockIdx.x, wl0 = blockIdx.y * 4;
+    const int t = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < REO_TILE) ghash[tid] = reo_mix32(seed_lo ^ ((uint32_t)(t * REO_TILE + tid) * 0x9E3779B1u));
+    for (int wl0 = blockIdx.y * 4; wl0 < w_n; wl0 += gridDim.y * 4) {   // gridDim.y is capped at 65535
+    __syncthreads();
     if (tid < 128) {
         const int wl = wl0 + (tid >> 5);
         so_s[tid] = wl < w_n ? sample_of_slot[(int64_t)(w_lo + wl) * 32 + (tid & 31)] : -1;
@@ -351,7 +355,7 @@ bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
     __syncthreads();
     const int q = wid >> 1, hf = wid & 1;               // this warp: sample word q of the CTA, genes hf*32 .. hf*32+31
     const int wl = wl0 + q;
-    if (wl >= w_n) return;
+    if (wl >= w_n) continue;
     const int row = q * 32 + lane;
     const int so = so_s[row];
     const uint32_t sterm = (uint32_t)so * 0x85EBCA77u + seed_hi;
@@ -377,13 +381,14 @@ bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
 #pragma unroll
     for (int p = 0; p < NPB; ++p)
         if (p < NP) out[(size_t)p * REO_TILE] = mine[p];
+    }
 }
 
 cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
                                  int NT, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo, uint32_t seed_hi,
                                  uint32_t* planes, cudaStream_t st) {
     if (w_n <= 0) return cudaSuccess;
-    dim3 grid(NT, (w_n + 3) / 4), block(256);
+    dim3 grid(NT, std::min((w_n + 3) / 4, 65535)), block(256);
 #define LAUNCH_BP(RT, NPB) bitplanes_kernel<RT, NPB><<<grid, block, 0, st>>>((const RT*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, seed_lo, seed_hi, planes)
 #define LAUNCH_BPN(RT)                                                                                                 \
     if (NP <= 5) LAUNCH_BP(RT, 5); else if (NP <= 9) LAUNCH_BP(RT, 9); else if (NP <= 13) LAUNCH_BP(RT, 13);           \
@@ -425,10 +430,12 @@ cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const
 template <typename T>
 __global__ void __launch_bounds__(256)
 fstage_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* __restrict__ sample_of_slot,
-              const int32_t* __restrict__ col_of_sample, int w_lo, int w_stride, uint32_t seed_lo, uint32_t seed_hi,
+              const int32_t* __restrict__ col_of_sample, int w_lo, int w_n, int w_stride, uint32_t seed_lo, uint32_t seed_hi,
               uint32_t* __restrict__ planes) {
-    const int t = blockIdx.x, wl = blockIdx.y, w = w_lo + wl, l = threadIdx.x, y = threadIdx.y;
+    const int t = blockIdx.x, l = threadIdx.x, y = threadIdx.y;
     const int64_t g = (int64_t)t * REO_TILE + l;
+    for (int wl = blockIdx.y; wl < w_n; wl += gridDim.y) {      // gridDim.y is capped at 65535
+    const int w = w_lo + wl;
     uint32_t* base = planes + ((size_t)t * w_stride + wl) * REO_FLT_OPWORDS;
     double* vals = reinterpret_cast<double*>(base + REO_TILE);
     for (int sidx = y; sidx < 32; sidx += 4) {
@@ -447,16 +454,17 @@ fstage_kernel(const T* __restrict__ data, int64_t r, int64_t ld, const int32_t* 
         }
         base[l] = coin;
     }
+    }
 }
 
 cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld, const int32_t* sample_of_slot,
                               const int32_t* col_of_sample, int NT, int w_lo, int w_n, int w_stride, uint32_t seed_lo,
                               uint32_t seed_hi, uint32_t* planes, cudaStream_t st) {
     if (w_n <= 0) return cudaSuccess;
-    dim3 grid(NT, w_n), block(REO_TILE, 4);
+    dim3 grid(NT, std::min(w_n, 65535)), block(REO_TILE, 4);
     switch (dtype) {
-        case REO_F64: fstage_kernel<double><<<grid, block, 0, st>>>((const double*)data, r, ld, sample_of_slot, col_of_sample, w_lo, w_stride, seed_lo, seed_hi, planes); break;
-        case REO_F32: fstage_kernel<float><<<grid, block, 0, st>>>((const float*)data, r, ld, sample_of_slot, col_of_sample, w_lo, w_stride, seed_lo, seed_hi, planes); break;
+        case REO_F64: fstage_kernel<double><<<grid, block, 0, st>>>((const double*)data, r, ld, sample_of_slot, col_of_sample, w_lo, w_n, w_stride, seed_lo, seed_hi, planes); break;
+        case REO_F32: fstage_kernel<float><<<grid, block, 0, st>>>((const float*)data, r, ld, sample_of_slot, col_of_sample, w_lo, w_n, w_stride, seed_lo, seed_hi, planes); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -466,20 +474,22 @@ cudaError_t reo_launch_fstage(const void* data, int dtype, int64_t r, int64_t ld
 __global__ void __launch_bounds__(256)
 gather_panel_flt_kernel(const uint32_t* __restrict__ planes, int W, const int32_t* __restrict__ col_gene,
                         uint32_t* __restrict__ panel) {
-    const int tc = blockIdx.x, w = blockIdx.y, l = threadIdx.x & 63, y = threadIdx.x >> 6;
+    const int tc = blockIdx.x, l = threadIdx.x & 63, y = threadIdx.x >> 6;
     const int g = col_gene[tc * REO_TILE + l];
+    for (int w = blockIdx.y; w < W; w += gridDim.y) {            // gridDim.y is capped at 65535
     const uint32_t* src = g >= 0 ? planes + ((size_t)(g >> 6) * W + w) * REO_FLT_OPWORDS : nullptr;
     uint32_t* dst = panel + ((size_t)tc * W + w) * REO_FLT_OPWORDS;
     if (y == 0) dst[l] = src ? src[g & 63] : 0u;
     const double* sv = src ? reinterpret_cast<const double*>(src + REO_TILE) : nullptr;
     double* dv = reinterpret_cast<double*>(dst + REO_TILE);
     for (int sidx = y; sidx < 32; sidx += 4) dv[sidx * REO_TILE + l] = sv ? sv[sidx * REO_TILE + (g & 63)] : 0.0;
+    }
 }
 
 cudaError_t reo_launch_gather_panel_flt(const uint32_t* planes, int W, const int32_t* col_gene, int ntc, uint32_t* panel,
                                         cudaStream_t st) {
     if (ntc <= 0) return cudaSuccess;
-    dim3 grid(ntc, W);
+    dim3 grid(ntc, std::min(W, 65535));
     gather_panel_flt_kernel<<<grid, 256, 0, st>>>(planes, W, col_gene, panel);
     return cudaGetLastError();
 }
@@ -489,15 +499,17 @@ cudaError_t reo_launch_gather_panel_flt(const uint32_t* planes, int W, const int
 __global__ void __launch_bounds__(256)
 unshard_planes_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ planes, int NT, int W, int wq, int wb4) {
     // one CTA per (tile, word); wb4 = operand words / 4 (16-byte units)
-    const int t = blockIdx.x, w = blockIdx.y;
-    const int q = w / wq, wl = w - q * wq;
-    const uint4* src = gathered + (((size_t)q * NT + t) * wq + wl) * wb4;
-    uint4* dst = planes + ((size_t)t * W + w) * wb4;
-    for (int i = threadIdx.x; i < wb4; i += blockDim.x) dst[i] = src[i];
+    const int t = blockIdx.x;
+    for (int w = blockIdx.y; w < W; w += gridDim.y) {            // gridDim.y is capped at 65535
+        const int q = w / wq, wl = w - q * wq;
+        const uint4* src = gathered + (((size_t)q * NT + t) * wq + wl) * wb4;
+        uint4* dst = planes + ((size_t)t * W + w) * wb4;
+        for (int i = threadIdx.x; i < wb4; i += blockDim.x) dst[i] = src[i];
+    }
 }
 cudaError_t reo_launch_unshard_planes(const uint32_t* gathered, uint32_t* planes, int NT, int W, int wq, int wb,
                                       cudaStream_t st) {
-    dim3 grid(NT, W);
+    dim3 grid(NT, std::min(W, 65535));
     unshard_planes_kernel<<<grid, 256, 0, st>>>((const uint4*)gathered, (uint4*)planes, NT, W, wq, wb / 4);
     return cudaGetLastError();
 }

@@ -320,12 +320,8 @@ __device__ int std_leaf_bounds(int64_t lo0, int64_t hi0, int want, int64_t* lo_o
     return nl;
 }
 
-// One warp (CTA of 32) per leaf.  The leaf's values are staged in shared memory (coalesced) and then summed
-// strictly left to right -- f(a1) + f(a2), then + f(a_i) -- by every lane redundantly (broadcast LDS.128, so the
-// serial DADD chain is the only dependency).  Pass 0 sums x; the last CTA to arrive combines the leaves in tree
-// order into the mean and releases the others (all CTAs of this small grid are co-resident: nleaf <= 256 warps
-// on 148 SMs); pass 1 sums (x-mean)^2 and the last CTA combines again into se.  ws: [0..255] leaf sums,
-// [256] mean, then 3 uint32 (arrivals of pass 0, arrivals of pass 1, release flag), all zero between launches.
+// Sum of a leaf strictly left to right -- f(a1) + f(a2), then + f(a_i) -- by every lane redundantly (broadcast
+// LDS.128 from the warp's staging slice, so the serial DADD chain is the only dependency).
 __device__ __forceinline__ double std_seq_sum(const double* vals, int cnt) {
     double v = vals[0];
     int i = 1;
@@ -341,54 +337,42 @@ __device__ __forceinline__ double std_seq_sum(const double* vals, int cnt) {
     return v;
 }
 
-__global__ void __launch_bounds__(32)
-std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ ws,
-           double* __restrict__ se_out) {
-    __shared__ __align__(16) double vals[1024];
+// ONE CTA of STD_WARPS warps: warp w takes leaves w, w + STD_WARPS, ... (a leaf's values are staged in the warp's
+// slice of shared memory and summed strictly left to right); __syncthreads, thread 0 combines the leaf sums in tree
+// order into the mean; second round likewise for the squared deviations.  No inter-CTA synchronisation.
+#define STD_WARPS 16
+__global__ void __launch_bounds__(STD_WARPS * 32)
+std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, int nleaf, double* __restrict__ se_out) {
+    extern __shared__ __align__(16) double std_sm[];      // [STD_WARPS][1024] leaf staging
     __shared__ double buf[STD_MAX_LEAVES];
-    __shared__ StdFrame frames[64];
-    __shared__ int64_t b_lo, b_hi;
+    __shared__ StdFrame frames[STD_WARPS][64];
     __shared__ double mean_s;
-    unsigned int* sync = reinterpret_cast<unsigned int*>(ws + STD_MAX_LEAVES + 1);
-    const int lane = threadIdx.x;
-    if (lane == 0) std_leaf_bounds(lo0, hi0, blockIdx.x, &b_lo, &b_hi, frames);
-    __syncwarp();
-    const int64_t lo = b_lo, hi = b_hi, m_all = hi0 - lo0 + 1;
-    const int cnt = (int)(hi - lo + 1);                    // 1..1024
-    for (int i = lane; i < cnt; i += 32) vals[i] = sorted[lo + i];
-    __syncwarp();
-    const volatile double* vw = ws;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* vals = std_sm + (size_t)warp * 1024;
+    const int64_t m_all = hi0 - lo0 + 1;
     for (int pass = 0; pass < 2; ++pass) {
-        const double v = std_seq_sum(vals, cnt);
-        if (lane == 0) {
-            ws[blockIdx.x] = v;
-            __threadfence();
-            const bool last = (atomicAdd(&sync[pass], 1u) == gridDim.x - 1);
-            if (last) {
-                __threadfence();
-                for (int l = 0; l < (int)gridDim.x; ++l) buf[l] = vw[l];
-                const double tot = std_combine(lo0, hi0, buf, frames);
-                if (pass == 0) {
-                    ws[STD_MAX_LEAVES] = tot / (double)m_all;
-                    __threadfence();
-                    atomicExch(&sync[2], 1u);              // release the other leaves
-                } else {
-                    *se_out = sqrt(tot / (double)(m_all - 1));
-                    sync[0] = 0u; sync[1] = 0u; sync[2] = 0u;   // everybody is past the flag by now
-                }
+        const double mean = pass ? mean_s : 0.0;
+        for (int leaf = warp; leaf < nleaf; leaf += STD_WARPS) {
+            int64_t lo = 0, hi = 0;
+            if (lane == 0) std_leaf_bounds(lo0, hi0, leaf, &lo, &hi, frames[warp]);
+            lo = __shfl_sync(0xffffffffu, lo, 0); hi = __shfl_sync(0xffffffffu, hi, 0);
+            const int cnt = (int)(hi - lo + 1);                    // 1..1024
+            for (int i = lane; i < cnt; i += 32) {
+                const double x = sorted[lo + i];
+                if (pass) { const double d = x - mean; vals[i] = d * d; } else vals[i] = x;
             }
-            if (pass == 0) {
-                while (atomicAdd(&sync[2], 0u) == 0u) { }
-                __threadfence();
-                mean_s = vw[STD_MAX_LEAVES];
-            }
-        }
-        __syncwarp();
-        if (pass == 0) {
-            const double mean = mean_s;
-            for (int i = lane; i < cnt; i += 32) { const double d = vals[i] - mean; vals[i] = d * d; }
+            __syncwarp();
+            const double v = std_seq_sum(vals, cnt);
+            if (lane == 0) buf[leaf] = v;
             __syncwarp();
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double tot = std_combine(lo0, hi0, buf, frames[0]);
+            if (pass == 0) mean_s = tot / (double)m_all;
+            else *se_out = sqrt(tot / (double)(m_all - 1));
+        }
+        __syncthreads();
     }
 }
 
@@ -401,10 +385,18 @@ static int std_count_leaves(int64_t lo, int64_t hi) {
 cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_out, double* ws, cudaStream_t st) {
     // round(Int, r*0.05) : round(Int, r*0.95), 1-based inclusive, round-half-even on the FP64 product
     const int64_t lo = (int64_t)nearbyint((double)n * 0.05), hi = (int64_t)nearbyint((double)n * 0.95);
-    if (lo < 1 || hi > n || hi < lo || !ws) return cudaErrorInvalidValue;
+    if (lo < 1 || hi > n || hi < lo) return cudaErrorInvalidValue;
     const int nleaf = std_count_leaves(lo - 1, hi - 1);
     if (nleaf > STD_MAX_LEAVES) return cudaErrorInvalidValue;
-    std_kernel<<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws, se_out);
+    (void)ws;
+    static bool attr_set = false;
+    const int smem = STD_WARPS * 1024 * (int)sizeof(double);
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    std_kernel<<<1, STD_WARPS * 32, smem, st>>>(sorted, lo - 1, hi - 1, nleaf, se_out);
     return cudaGetLastError();
 }
 

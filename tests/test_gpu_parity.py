@@ -355,6 +355,26 @@ def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
             os.environ.pop("REO_K1_SHARD_MIN", None)
 
 
+def test_subset_and_detect_more_than_65535_cells(reo):
+    """gridDim.y is capped at 65535: the kernels next to the path stride over the cell dimension."""
+    rng = np.random.default_rng(3)
+    data = rng.integers(0, 3, size=(40, 70001)).astype(np.int32)
+    genes = np.arange(0, 40, 3)
+    cells = np.arange(70001)[::-1].copy()
+    out, _ = reo.subset(data, genes, cells)
+    assert np.array_equal(out, data[np.ix_(genes, cells)])
+    per_cell, per_gene = reo.detect_counts(data)
+    assert np.array_equal(per_cell, (data > 0).sum(axis=0)) and np.array_equal(per_gene, (data > 0).sum(axis=1))
+
+
+def test_no_threshold_is_an_error(reo):
+    """pval_reo >= 1: src:85 finds no count -- the reference throws, the library reports a bad argument."""
+    data, group = small_case(5, 60, 6, 7)
+    gid = np.array([0 if g == "a" else 1 for g in group], dtype=np.int32)
+    with pytest.raises(ValueError):
+        reo.identify_degs(data, gid, 2, np.ones(60, bool), 1.0, 1.0, 0.05, 4, 1)
+
+
 # ---- the UNMODIFIED reference's own outputs (tie-free inputs), when a maintainer with Julia has dumped them -------
 def test_reference_julia_fixtures(reo, oracle):
     """tests/golden/julia_out/<case>.tsv = RankCompV3.identify_degs run by julia/dump_reference_fixture.jl on the inputs
