@@ -299,8 +299,7 @@ LevelPlan make_plan(const ReoStaged& S, int k, const int32_t* thresholds, double
 
 int ensure_std_ws(reo_handle_t h, ReoDev& D) {
     if (D.std_ws.p) return REO_OK;
-    CK(D.std_ws.ensure(264));
-    CK(cudaMemsetAsync(D.std_ws.p, 0, 264 * sizeof(double), D.st));
+    CK(D.std_ws.ensure(2 * 256));   // leaf sums of the two passes (reo_launch_trimmed_std)
     return REO_OK;
 }
 
@@ -839,7 +838,7 @@ void drop_eval_graphs(ReoDev& D) {
 // (their launch gaps otherwise dominate).
 int run_eval(reo_handle_t h, ReoDev& D, int64_t r, double pval_deg, double padj_deg, uint8_t* mask_cur,
              uint8_t* mask_new, double* early_dst) {
-    h->kernel_launches += 8;  // mccullagh, sort x2, std, p_order, bh x2, diff
+    h->kernel_launches += 10;  // mccullagh, sort x2, std x3, p_order, bh x2, diff
     static const bool no_graph = getenv("REO_NO_GRAPH") != nullptr;
     CK(reo_sort_reserve(D.sortws, r, D.st));
     const int rc0 = enqueue_mcc(h, D, r, early_dst);

@@ -83,6 +83,7 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
                     const int32_t* __restrict__ src_col, const int32_t* __restrict__ sample_id,
                     const int32_t* __restrict__ slot_of_sample, RT* __restrict__ ranks, int64_t rpad,
                     int* max_distinct, int* flags, int* over_count, int32_t* over_list) {
+    constexpr bool ZB = (BMW == BM_WORDS_S);                 // small tier: bitmap indexed by the value itself
     constexpr int BMP = BMW / BM_GROUP;                      // prefix entries
     constexpr int BM_ITEMS = (BMP + NTHR - 1) / NTHR;
     constexpr int RK_THREADS_L = NTHR;
@@ -98,8 +99,40 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
     const int64_t s = sample_id[j];               // original sample index (slot lookup, fallback list)
     const T* __restrict__ col = data + ld * (int64_t)src_col[j];
 
+    long long mn = 0;
+    int nwords;
+    if (ZB) {
+        // small tier, ONE pass over global memory: counts are non-negative and small, so the bitmap is indexed by the
+        // value itself (no minimum to subtract: the dense rank does not depend on the offset).  A value outside
+        // [0, 32 * BMW) sends the column to the next tier, a non-integral one flags the matrix.
+        for (int w = tid; w < BMW; w += RK_THREADS_L) bm[w] = 0u;
+        __syncthreads();
+        int bad = 0, oor = 0;
+        for (int64_t g = tid; g < r; g += RK_THREADS_L) {
+            long long v;
+            if (!to_ll<T>(col[g], v)) { bad = 1; continue; }
+            if ((unsigned long long)v >= (unsigned long long)BMW * 32ull) { oor = 1; continue; }
+            const uint32_t k = (uint32_t)v;
+            if (STASH) stash[g] = (uint16_t)k;
+            const uint32_t bit = 1u << (k & 31);
+            // sparse counts put most genes on the same few values: test first, the atomic is the rare case
+            if (!(((volatile uint32_t*)bm)[k >> 5] & bit)) atomicOr(&bm[k >> 5], bit);
+        }
+        const int any_bad = __syncthreads_or(bad);      // (the result is a truth value, not a bitwise OR)
+        const int any_oor = __syncthreads_or(oor);
+        if (any_bad) {  // non-integral value: rank compression is not valid under the 0.1 tie band
+            if (tid == 0) atomicExch(&flags[0], 1);
+            return;
+        }
+        if (any_oor) {  // next tier
+            if (tid == 0) { int k = atomicAdd(over_count, 1); over_list[k] = (int32_t)j; }
+            return;
+        }
+        nwords = BMW;
+    } else {
     // phase 1: min / max / integrality
-    long long mn = LLONG_MAX, mx = LLONG_MIN;
+    long long mx = LLONG_MIN;
+    mn = LLONG_MAX;
     int bad = 0;
     for (int64_t g = tid; g < r; g += RK_THREADS_L) {
         long long v;
@@ -129,9 +162,11 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
         return;
     }
     // phase 2: presence bitmap of (v - min)
-    const int nwords = (int)(range >> 5) + 1;
-    const int ngroups = (nwords + BM_GROUP - 1) / BM_GROUP;
-    for (int w = tid; w < ngroups * BM_GROUP; w += RK_THREADS_L) bm[w] = 0u;
+    nwords = (int)(range >> 5) + 1;
+    {
+        const int ng = (nwords + BM_GROUP - 1) / BM_GROUP;
+        for (int w = tid; w < ng * BM_GROUP; w += RK_THREADS_L) bm[w] = 0u;
+    }
     __syncthreads();
     for (int64_t g = tid; g < r; g += RK_THREADS_L) {
         long long v; to_ll<T>(col[g], v);
@@ -142,6 +177,8 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
         if (!(((volatile uint32_t*)bm)[k >> 5] & bit)) atomicOr(&bm[k >> 5], bit);
     }
     __syncthreads();
+    }
+    const int ngroups = (nwords + BM_GROUP - 1) / BM_GROUP;
     // phase 3: exclusive prefix of popcounts per group of BM_GROUP words
     int loc[BM_ITEMS];
     int sum = 0;
@@ -178,6 +215,74 @@ rank_columns_kernel(const T* __restrict__ data, int64_t r, int64_t ld, int64_t c
         out[g] = (RT)rk;
     }
 }
+
+// ---- small tier, specialised: values in [0, 65536), up to RK_STASH_MAX_R genes, u16 ranks ---------------------------
+// The common case (counts; single-cell data in particular).  One CTA per sample column, ONE pass over global memory:
+// two genes per thread and iteration, the values go into a presence bitmap indexed by the value itself and are parked
+// as u16 pairs in shared memory; a per-word prefix of the bitmap popcounts then turns every parked value into its dense
+// rank with two shared-memory reads, and the ranks leave as u16 pairs.  32-bit index arithmetic throughout.
+template <typename T>
+__global__ void __launch_bounds__(RK_THREADS, 2)
+rank_small_kernel(const T* __restrict__ data, int r, int64_t ld, int64_t col0, const int32_t* __restrict__ src_col,
+                  const int32_t* __restrict__ sample_id, const int32_t* __restrict__ slot_of_sample,
+                  uint16_t* __restrict__ ranks, int64_t rpad, int* max_distinct, int* flags, int* over_count,
+                  int32_t* over_list) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* bm = sm;                                   // [BM_WORDS_S] presence bitmap of the values
+    uint32_t* prew = sm + BM_WORDS_S;                    // [BM_WORDS_S] distinct values below word w
+    int* red = (int*)(prew + BM_WORDS_S);                // [40]
+    uint32_t* stash = (uint32_t*)(red + 40);             // [(r + 1) / 2] two parked values per word
+    const int tid = threadIdx.x;
+    const int64_t j = col0 + blockIdx.x;                 // position in this rank's column list
+    const T* __restrict__ col = data + ld * (int64_t)src_col[j];
+    for (int w = tid; w < BM_WORDS_S; w += RK_THREADS) bm[w] = 0u;
+    __syncthreads();
+    const int npair = (r + 1) >> 1;
+    int bad = 0, oor = 0;
+    for (int i = tid; i < npair; i += RK_THREADS) {
+        const int g = 2 * i;
+        const bool two = g + 1 < r;
+        long long v0 = 0, v1 = 0;
+        if (!to_ll<T>(col[g], v0)) { bad = 1; v0 = 0; }
+        if (two && !to_ll<T>(col[g + 1], v1)) { bad = 1; v1 = 0; }
+        if (((unsigned long long)v0 | (unsigned long long)v1) >= (unsigned long long)BM_WORDS_S * 32ull) { oor = 1; continue; }
+        const uint32_t k0 = (uint32_t)v0, k1 = (uint32_t)v1;
+        stash[i] = k0 | (k1 << 16);
+        // sparse counts put most genes on the same few values: test first, the atomic is the rare case
+        const uint32_t b0 = 1u << (k0 & 31), b1 = 1u << (k1 & 31);
+        if (!(((volatile uint32_t*)bm)[k0 >> 5] & b0)) atomicOr(&bm[k0 >> 5], b0);
+        if (two && !(((volatile uint32_t*)bm)[k1 >> 5] & b1)) atomicOr(&bm[k1 >> 5], b1);
+    }
+    const int any_bad = __syncthreads_or(bad);
+    const int any_oor = __syncthreads_or(oor);
+    if (any_bad) {  // non-integral value: rank compression is not valid under the 0.1 tie band
+        if (tid == 0) atomicExch(&flags[0], 1);
+        return;
+    }
+    if (any_oor) {  // next tier
+        if (tid == 0) { int k = atomicAdd(over_count, 1); over_list[k] = (int32_t)j; }
+        return;
+    }
+    {   // exclusive prefix of the popcounts, two bitmap words per thread (BM_WORDS_S == 2 * RK_THREADS)
+        const int c0 = __popc(bm[2 * tid]), c1 = __popc(bm[2 * tid + 1]);
+        int total;
+        const int base = block_excl_scan(c0 + c1, red, &total);
+        prew[2 * tid] = (uint32_t)base;
+        prew[2 * tid + 1] = (uint32_t)(base + c0);
+        if (tid == 0) atomicMax(max_distinct, total);
+    }
+    __syncthreads();
+    const int64_t slot = slot_of_sample[sample_id[j]];
+    uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(ranks + slot * rpad);   // rpad is a multiple of 64
+    for (int i = tid; i < npair; i += RK_THREADS) {
+        const uint32_t st = stash[i];
+        const uint32_t k0 = st & 0xffffu, k1 = st >> 16;
+        const uint32_t r0 = prew[k0 >> 5] + (uint32_t)__popc(bm[k0 >> 5] & ((1u << (k0 & 31)) - 1u));
+        const uint32_t r1 = prew[k1 >> 5] + (uint32_t)__popc(bm[k1 >> 5] & ((1u << (k1 & 31)) - 1u));
+        out[i] = r0 | (r1 << 16);
+    }
+}
+static_assert(BM_WORDS_S == 2 * RK_THREADS, "rank_small_kernel scans two bitmap words per thread");
 
 // ---- fallback: sort-based dense rank in a global-memory scratch (rare: value range > bitmap) ----
 template <typename T, typename RT>
@@ -254,6 +359,12 @@ static cudaError_t launch_rank_t(const void* data, int64_t r, int64_t ld, int64_
         rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS, false><<<ncols, RK_THREADS, smem, st>>>(
             (const T*)data, r, ld, col0, cols, src_col, sample_id, slot_of_sample, (RT*)ranks, rpad, max_distinct, flags,
             over_count, over_list);
+    } else if (r <= RK_STASH_MAX_R && sizeof(RT) == 2 && cols == nullptr) {
+        const size_t smem = (size_t)(2 * BM_WORDS_S + 40) * 4 + (size_t)((r + 1) / 2) * 4 + 16;
+        e = cudaFuncSetAttribute(rank_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rank_small_kernel<T><<<ncols, RK_THREADS, smem, st>>>((const T*)data, (int)r, ld, col0, src_col, sample_id, slot_of_sample,
+                                                              (uint16_t*)ranks, rpad, max_distinct, flags, over_count, over_list);
     } else if (r <= RK_STASH_MAX_R) {
         const size_t smem = rank_smem_bytes(BM_WORDS_S) + (size_t)r * 2 + 16;
         e = cudaFuncSetAttribute(rank_columns_kernel<T, RT, RK_THREADS, BM_WORDS_S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -312,75 +423,87 @@ cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int
 }
 
 // ---- bit-plane transpose ------------------------------------------------------------------------
-// CTA = gene tile t x 4 sample words (128 slots), 256 threads.  The 128 x 64 ranks are loaded with genes along the
-// lanes (coalesced), parked in shared memory and read back with SAMPLES along the lanes, so one __ballot_sync per
-// plane turns 32 samples of one gene into the finished word; lane j keeps the words of gene j and the stores are
-// coalesced again.  Cost per (gene, sample): the coin hash (~9 integer ops) + (NPB x 3 + 2) / 32 instructions.
-// NPB = compile-time bound on the plane count (NP <= NPB): the plane loop must unroll over exactly the planes in use.
-template <typename RT, int NPB>
+// 32 x 32 bit-matrix transpose across the lanes of a warp (5 butterfly steps): on entry lane s holds row s, on exit
+// lane b holds column b, i.e. bit s of the result is bit b of lane s's input.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = (j == 16) ? 0x0000FFFFu : (j == 8) ? 0x00FF00FFu : (j == 4) ? 0x0F0F0F0Fu
+                                                               : (j == 2) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+    }
+    return x;
+}
+
+// CTA = one sample word (32 slots) x GC = 256 * PER genes (8 tiles of u16 ranks, 4 tiles of u32 ranks), 256 threads.
+// The 32 x GC ranks are loaded with genes along the lanes (1 KB contiguous per slot row) and parked in shared memory;
+// a warp then takes GC / 8 genes with lane = sample slot: it packs GPW = 32 / FW genes into a word per lane -- FW-bit
+// fields [rank : coin], FW >= planes -- and transposes the 32 x 32 bits across its lanes, so that lane (gene k, plane p)
+// ends up with the finished 32-sample word.  Cost per (gene, sample): the coin hash (7 integer ops) + ~5 instructions
+// for unpacking, packing and transposing (the first version spent 3 instructions per plane on ballots).  Output goes
+// through shared memory: 256-byte coalesced stores per (tile, plane).
+template <typename RT, int FW>
 __global__ void __launch_bounds__(256)
 bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
                  const int32_t* __restrict__ sample_of_slot, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo,
                  uint32_t seed_hi, uint32_t* __restrict__ planes) {
     // words [w_lo, w_lo + w_n) of the staged order are written at local index (w - w_lo) with w_stride words per tile
     constexpr int PER = 4 / sizeof(RT);                 // ranks per 32-bit word
-    constexpr int LD = REO_TILE / PER + 1;              // row stride in words, odd: conflict-free column reads
-    __shared__ uint32_t tile[128 * LD];                 // [slot][gene]
-    __shared__ uint32_t ghash[REO_TILE];                // inner hash of the coin, per gene
-    __shared__ int so_s[128];
-    const int t = blockIdx.x;
+    constexpr int GC = 256 * PER;                       // genes per CTA
+    constexpr int TPC = GC / REO_TILE;                  // gene tiles per CTA
+    constexpr int GW = GC / 8;                          // genes per warp
+    constexpr int LDW = 256 + 1;                        // row stride in words, odd: conflict-free column reads
+    constexpr int GPW = 32 / FW;                        // genes per transposed word
+    constexpr int OS = REO_TILE + 8;                    // plane stride of the output staging
+    extern __shared__ uint32_t bp_sm[];
+    uint32_t* tile = bp_sm;                             // [32 slots][LDW]
+    uint32_t* ghash = tile + 32 * LDW;                  // [GC] inner hash of the coin, per gene
+    uint32_t* outs = ghash + GC;                        // [TPC][NP][OS]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < REO_TILE) ghash[tid] = reo_mix32(seed_lo ^ ((uint32_t)(t * REO_TILE + tid) * 0x9E3779B1u));
-    for (int wl0 = blockIdx.y * 4; wl0 < w_n; wl0 += gridDim.y * 4) {   // gridDim.y is capped at 65535
-    __syncthreads();
-    if (tid < 128) {
-        const int wl = wl0 + (tid >> 5);
-        so_s[tid] = wl < w_n ? sample_of_slot[(int64_t)(w_lo + wl) * 32 + (tid & 31)] : -1;
-    }
-    __syncthreads();
-    const int64_t gbase = (int64_t)t * REO_TILE;
-    for (int idx = tid; idx < 128 * (REO_TILE / PER); idx += 256) {
-        const int row = idx / (REO_TILE / PER), cw = idx % (REO_TILE / PER);
-        uint32_t v = 0u;
-        if (so_s[row] >= 0) {
-            const int64_t S = (int64_t)(w_lo + wl0 + (row >> 5)) * 32 + (row & 31);
-            const int64_t g0 = gbase + (int64_t)cw * PER;
-            if (g0 < r) {
-                v = *reinterpret_cast<const uint32_t*>(ranks + S * rpad + g0);   // rpad is a multiple of 64: aligned
-                if (PER == 2 && g0 + 1 >= r) v &= 0xffffu;                       // genes >= r are not ranked
-            }
+    const int64_t gbase = (int64_t)blockIdx.x * GC;
+    for (int i = tid; i < GC; i += 256) ghash[i] = reo_mix32(seed_lo ^ ((uint32_t)(gbase + i) * 0x9E3779B1u));
+    for (int wl = blockIdx.y; wl < w_n; wl += gridDim.y) {   // gridDim.y is capped at 65535
+        __syncthreads();
+        const int so = sample_of_slot[(int64_t)(w_lo + wl) * 32 + lane];      // this lane's sample (pack phase), -1 = pad slot
+        const int64_t g0 = gbase + (int64_t)tid * PER;
+#pragma unroll 4
+        for (int row = 0; row < 32; ++row) {
+            const int so_r = __shfl_sync(0xffffffffu, so, row);
+            uint32_t v = 0u;
+            if (so_r >= 0 && g0 < rpad)
+                v = *reinterpret_cast<const uint32_t*>(ranks + ((int64_t)(w_lo + wl) * 32 + row) * rpad + g0);
+            tile[row * LDW + tid] = v;
         }
-        tile[row * LD + cw] = v;
-    }
-    __syncthreads();
-    const int q = wid >> 1, hf = wid & 1;               // this warp: sample word q of the CTA, genes hf*32 .. hf*32+31
-    const int wl = wl0 + q;
-    if (wl >= w_n) continue;
-    const int row = q * 32 + lane;
-    const int so = so_s[row];
-    const uint32_t sterm = (uint32_t)so * 0x85EBCA77u + seed_hi;
-    uint32_t mine[NPB];
-#pragma unroll
-    for (int p = 0; p < NPB; ++p) mine[p] = 0u;
+        __syncthreads();
+        const uint32_t sterm = (uint32_t)so * 0x85EBCA77u + seed_hi;
+        const uint32_t slotmask = __ballot_sync(0xffffffffu, so >= 0);
+        const int myp = lane % FW, myk = lane / FW;     // after the transpose: this lane's plane and gene in the group
+        const uint32_t* trow = tile + lane * LDW;
 #pragma unroll 2
-    for (int j = 0; j < 32; ++j) {
-        const int gi = hf * 32 + j;
-        uint32_t rk = tile[row * LD + gi / PER];
-        if (PER == 2) rk = (gi & 1) ? (rk >> 16) : (rk & 0xffffu);
-        const bool live = so >= 0 && gbase + gi < r;
-        const uint32_t coin = live ? (reo_mix32(ghash[gi] + sterm) >> 31) : 0u;
-        const uint32_t w0 = __ballot_sync(0xffffffffu, coin);
-        if (lane == j) mine[0] = w0;
+        for (int grp = 0; grp < GW / GPW; ++grp) {
+            uint32_t x = 0u;
 #pragma unroll
-        for (int p = 1; p < NPB; ++p) {                  // planes >= NP come out zero (rk < 2^(NP-1)) and are not stored
-            const uint32_t wv = __ballot_sync(0xffffffffu, (rk & (1u << (p - 1))) != 0u);
-            if (lane == j) mine[p] = wv;
+            for (int k = 0; k < GPW; ++k) {
+                const int gi = wid * GW + grp * GPW + k;                      // gene within the CTA
+                uint32_t rk = trow[gi / PER];
+                if (PER == 2) rk = (gi & 1) ? (rk >> 16) : (rk & 0xffffu);
+                const uint32_t coin = reo_mix32(ghash[gi] + sterm) >> 31;
+                x |= ((rk << 1) | coin) << (k * FW);
+            }
+            x = warp_transpose32(x, lane) & slotmask;                        // pad slots contribute nothing
+            const int gq = wid * GW + grp * GPW + myk;                        // this lane's gene within the CTA
+            if (gbase + gq >= r) x = 0u;                                      // genes >= r are not ranked
+            if (myp < NP) outs[((gq >> 6) * NP + myp) * OS + (gq & 63)] = x;
         }
-    }
-    uint32_t* out = planes + ((size_t)t * w_stride + wl) * NP * REO_TILE + hf * 32 + lane;
-#pragma unroll
-    for (int p = 0; p < NPB; ++p)
-        if (p < NP) out[(size_t)p * REO_TILE] = mine[p];
+        __syncthreads();
+        for (int idx = tid; idx < TPC * NP * REO_TILE; idx += 256) {
+            const int tp = idx / REO_TILE, l = idx - tp * REO_TILE;           // tp = tile-in-CTA * NP + plane
+            const int tl = tp / NP;
+            const int64_t t = (int64_t)blockIdx.x * TPC + tl;
+            if (t * REO_TILE < rpad)
+                planes[((size_t)t * w_stride + wl) * NP * REO_TILE + (size_t)(tp - tl * NP) * REO_TILE + l] = outs[tp * OS + l];
+        }
     }
 }
 
@@ -388,11 +511,18 @@ cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad
                                  int NT, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo, uint32_t seed_hi,
                                  uint32_t* planes, cudaStream_t st) {
     if (w_n <= 0) return cudaSuccess;
-    dim3 grid(NT, std::min((w_n + 3) / 4, 65535)), block(256);
-#define LAUNCH_BP(RT, NPB) bitplanes_kernel<RT, NPB><<<grid, block, 0, st>>>((const RT*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, seed_lo, seed_hi, planes)
+    const int per = 4 / rank_bytes, gc = 256 * per, tpc = gc / REO_TILE;
+    dim3 grid((NT + tpc - 1) / tpc, std::min(w_n, 65535)), block(256);
+    const size_t smem = ((size_t)32 * 257 + gc + (size_t)tpc * NP * (REO_TILE + 8)) * sizeof(uint32_t);
+#define LAUNCH_BP(RT, FW)                                                                                              \
+    do {                                                                                                               \
+        cudaError_t e_ = cudaFuncSetAttribute(bitplanes_kernel<RT, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e_ != cudaSuccess) return e_;                                                                              \
+        bitplanes_kernel<RT, FW><<<grid, block, smem, st>>>((const RT*)ranks, rpad, r, sample_of_slot, w_lo, w_n, w_stride, NP, \
+                                                            seed_lo, seed_hi, planes);                                 \
+    } while (0)
 #define LAUNCH_BPN(RT)                                                                                                 \
-    if (NP <= 5) LAUNCH_BP(RT, 5); else if (NP <= 9) LAUNCH_BP(RT, 9); else if (NP <= 13) LAUNCH_BP(RT, 13);           \
-    else if (NP <= 17) LAUNCH_BP(RT, 17); else LAUNCH_BP(RT, REO_MAX_PLANES)
+    if (NP <= 8) LAUNCH_BP(RT, 8); else if (NP <= 16) LAUNCH_BP(RT, 16); else LAUNCH_BP(RT, 32)
     if (rank_bytes == 2) { LAUNCH_BPN(uint16_t); } else { LAUNCH_BPN(uint32_t); }
 #undef LAUNCH_BPN
 #undef LAUNCH_BP

@@ -320,60 +320,62 @@ __device__ int std_leaf_bounds(int64_t lo0, int64_t hi0, int want, int64_t* lo_o
     return nl;
 }
 
-// Sum of a leaf strictly left to right -- f(a1) + f(a2), then + f(a_i) -- by every lane redundantly (broadcast
-// LDS.128 from the warp's staging slice, so the serial DADD chain is the only dependency).
-__device__ __forceinline__ double std_seq_sum(const double* vals, int cnt) {
-    double v = vals[0];
-    int i = 1;
-    if (cnt > 1) { v = v + vals[1]; i = 2; }               // pairs from here on are 16-byte aligned
-    const double2* v2 = reinterpret_cast<const double2*>(vals);
-#pragma unroll 8
-    for (; i + 1 < cnt; i += 2) {
-        const double2 t = v2[i >> 1];
-        v = v + t.x;
-        v = v + t.y;
+// Three small launches, no inter-CTA waiting (the first version spun on a flag between its two passes):
+//   std_leaf_kernel<0>  one warp (CTA of 32) per leaf: sum of the leaf's values                      -> ws[leaf]
+//   std_leaf_kernel<1>  every CTA first combines ws[] in tree order into the mean (redundantly: <= 256 adds), then
+//                       sums its leaf's squared deviations                                          -> ws[256 + leaf]
+//   std_final_kernel    combines those in tree order                                                -> se
+// A leaf is summed strictly left to right -- f(a1) + f(a2), then + f(a_i) -- 32 values at a time: every lane loads one,
+// the values are handed round with shuffles (off the dependency chain) and every lane carries the same running sum, so
+// the serial DADD chain is the only dependency.  Leaves run on different SMs: the FP64 pipe of one SM is not shared.
+__device__ __forceinline__ double std_leaf_sum(const double* __restrict__ sorted, int64_t lo, int cnt, int lane, bool sq, double mean) {
+    double v = 0.0;
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        double x = 0.0;
+        if (c0 + lane < cnt) {
+            x = sorted[lo + c0 + lane];
+            if (sq) { const double d = x - mean; x = d * d; }
+        }
+        const int n = min(32, cnt - c0);
+        if (c0 == 0) {                                      // the first element starts the sum (no 0.0 + a1)
+            v = __shfl_sync(0xffffffffu, x, 0);
+            for (int k = 1; k < n; ++k) v = v + __shfl_sync(0xffffffffu, x, k);
+        } else if (n == 32) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v = v + __shfl_sync(0xffffffffu, x, k);
+        } else {
+            for (int k = 0; k < n; ++k) v = v + __shfl_sync(0xffffffffu, x, k);
+        }
     }
-    if (i < cnt) v = v + vals[i];
     return v;
 }
 
-// ONE CTA of STD_WARPS warps: warp w takes leaves w, w + STD_WARPS, ... (a leaf's values are staged in the warp's
-// slice of shared memory and summed strictly left to right); __syncthreads, thread 0 combines the leaf sums in tree
-// order into the mean; second round likewise for the squared deviations.  No inter-CTA synchronisation.
-#define STD_WARPS 16
-__global__ void __launch_bounds__(STD_WARPS * 32)
-std_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, int nleaf, double* __restrict__ se_out) {
-    extern __shared__ __align__(16) double std_sm[];      // [STD_WARPS][1024] leaf staging
+template <int PASS>
+__global__ void __launch_bounds__(32)
+std_leaf_kernel(const double* __restrict__ sorted, int64_t lo0, int64_t hi0, double* __restrict__ ws) {
+    __shared__ StdFrame frames[64];
     __shared__ double buf[STD_MAX_LEAVES];
-    __shared__ StdFrame frames[STD_WARPS][64];
+    __shared__ int64_t b_lo, b_hi;
     __shared__ double mean_s;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* vals = std_sm + (size_t)warp * 1024;
-    const int64_t m_all = hi0 - lo0 + 1;
-    for (int pass = 0; pass < 2; ++pass) {
-        const double mean = pass ? mean_s : 0.0;
-        for (int leaf = warp; leaf < nleaf; leaf += STD_WARPS) {
-            int64_t lo = 0, hi = 0;
-            if (lane == 0) std_leaf_bounds(lo0, hi0, leaf, &lo, &hi, frames[warp]);
-            lo = __shfl_sync(0xffffffffu, lo, 0); hi = __shfl_sync(0xffffffffu, hi, 0);
-            const int cnt = (int)(hi - lo + 1);                    // 1..1024
-            for (int i = lane; i < cnt; i += 32) {
-                const double x = sorted[lo + i];
-                if (pass) { const double d = x - mean; vals[i] = d * d; } else vals[i] = x;
-            }
-            __syncwarp();
-            const double v = std_seq_sum(vals, cnt);
-            if (lane == 0) buf[leaf] = v;
-            __syncwarp();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const double tot = std_combine(lo0, hi0, buf, frames[0]);
-            if (pass == 0) mean_s = tot / (double)m_all;
-            else *se_out = sqrt(tot / (double)(m_all - 1));
-        }
-        __syncthreads();
+    const int lane = threadIdx.x;
+    if (PASS == 1) for (int l = lane; l < (int)gridDim.x; l += 32) buf[l] = ws[l];
+    __syncwarp();
+    if (lane == 0) {
+        std_leaf_bounds(lo0, hi0, blockIdx.x, &b_lo, &b_hi, frames);
+        if (PASS == 1) mean_s = std_combine(lo0, hi0, buf, frames) / (double)(hi0 - lo0 + 1);
     }
+    __syncwarp();
+    const double v = std_leaf_sum(sorted, b_lo, (int)(b_hi - b_lo + 1), lane, PASS == 1, PASS == 1 ? mean_s : 0.0);
+    if (lane == 0) ws[PASS * STD_MAX_LEAVES + blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(32)
+std_final_kernel(int64_t lo0, int64_t hi0, int nleaf, const double* __restrict__ ws, double* __restrict__ se_out) {
+    __shared__ StdFrame frames[64];
+    __shared__ double buf[STD_MAX_LEAVES];
+    for (int l = threadIdx.x; l < nleaf; l += 32) buf[l] = ws[STD_MAX_LEAVES + l];
+    __syncwarp();
+    if (threadIdx.x == 0) *se_out = sqrt(std_combine(lo0, hi0, buf, frames) / (double)(hi0 - lo0));
 }
 
 static int std_count_leaves(int64_t lo, int64_t hi) {
@@ -388,15 +390,10 @@ cudaError_t reo_launch_trimmed_std(const double* sorted, int64_t n, double* se_o
     if (lo < 1 || hi > n || hi < lo) return cudaErrorInvalidValue;
     const int nleaf = std_count_leaves(lo - 1, hi - 1);
     if (nleaf > STD_MAX_LEAVES) return cudaErrorInvalidValue;
-    (void)ws;
-    static bool attr_set = false;
-    const int smem = STD_WARPS * 1024 * (int)sizeof(double);
-    if (!attr_set) {
-        const cudaError_t e = cudaFuncSetAttribute(std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    std_kernel<<<1, STD_WARPS * 32, smem, st>>>(sorted, lo - 1, hi - 1, nleaf, se_out);
+    if (!ws) return cudaErrorInvalidValue;            // 2 * STD_MAX_LEAVES doubles
+    std_leaf_kernel<0><<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws);
+    std_leaf_kernel<1><<<nleaf, 32, 0, st>>>(sorted, lo - 1, hi - 1, ws);
+    std_final_kernel<<<1, 32, 0, st>>>(lo - 1, hi - 1, nleaf, ws, se_out);
     return cudaGetLastError();
 }
 

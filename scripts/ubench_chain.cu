@@ -64,9 +64,12 @@ template <int NBT, int NP, bool PF, bool PACK>
 void run(const char* name, int ctas_per_sm, uint32_t* out, int sms, double mhz) {
     auto kern = chain_kernel<NBT, NP, PF, PACK>;
     // shared memory sized so that exactly ctas_per_sm CTAs are resident
+    const int need = 8 * 3 * NP * 256;                       // the kernel's own footprint
     const int smem = (227 * 1024) / ctas_per_sm - 1024;
+    if (smem < need) { printf("%-28s needs %d KB of shared memory: %d CTAs/SM do not fit\n", name, need / 1024, ctas_per_sm); return; }
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+    if (occ < 1) { printf("%-28s does not fit\n", name); return; }
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
     const int words = 20000, grid = sms * occ;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
