@@ -133,6 +133,12 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
 int reo_iter_log(reo_handle_t h, int32_t k, int32_t* iters_done, int32_t* converged, int32_t* n_deg, int32_t* n_ref,
                  int32_t cap);
 
+/* Test hook, host only (no GPU): the (row tile, column tile, update flags) triples rank `rank` of `world` evaluates for
+ * a table build over `ncols` of `r` genes, replayed from the library's own partition code (csrc/reo_pairs2.cu).  See the
+ * definition in csrc/reo_api.cu; used by tests/test_dist_gloo.py to check the multi-rank partition on CPU. */
+long long reo_debug_pair_plan(int64_t r, int64_t ncols, int32_t sample_words, int32_t planes, int32_t rank, int32_t world,
+                              int32_t mode, int32_t* out, int64_t cap, int32_t* nsym_tiles, int32_t* ntr, int32_t* ntc);
+
 /* ---- stage-level entry points (parity tests, benches, profilers) ------------------------- */
 
 /* K1: copy, dense-rank per sample, bit-slice, coin plane.  The staged matrix stays resident in

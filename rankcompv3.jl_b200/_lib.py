@@ -27,7 +27,7 @@ REO_MAX_ITER_LOG = 256
 SYMBOLS = [
     "reo_version", "reo_create", "reo_destroy", "reo_last_error", "reo_set_collective", "reo_comm_unique_id",
     "reo_comm_init_rank", "reo_host_alloc", "reo_host_free", "reo_threshold",
-    "reo_identify_degs", "reo_iter_log", "reo_stage", "reo_stage_info", "reo_pair_counts", "reo_tables", "reo_tables_delta",
+    "reo_identify_degs", "reo_iter_log", "reo_debug_pair_plan", "reo_stage", "reo_stage_info", "reo_pair_counts", "reo_tables", "reo_tables_delta",
     "reo_mccullagh", "reo_empirical_null", "reo_bh", "reo_sort_f64", "reo_pseudobulk", "reo_detect_counts", "reo_subset",
 ]
 
@@ -93,6 +93,8 @@ def load():
                                     vp, vp, vp, vp, C.POINTER(ReoStats)]
     L.reo_iter_log.restype = C.c_int
     L.reo_iter_log.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), vp, vp, i32]
+    L.reo_debug_pair_plan.restype = C.c_longlong
+    L.reo_debug_pair_plan.argtypes = [i64, i64, i32, i32, i32, i32, i32, vp, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.reo_stage.restype = C.c_int
     L.reo_stage.argtypes = [vp, vp, C.c_int, i64, i64, i64, vp, i32, u32]
     L.reo_stage_info.restype = C.c_int

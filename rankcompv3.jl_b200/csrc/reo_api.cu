@@ -1312,6 +1312,31 @@ int reo_subset(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c
     return REO_OK;
 }
 
+/* Test hook (CPU, no GPU needed): the tile pairs rank `rank` of `world` evaluates for a table build over `ncols` column
+ * genes out of `r` genes staged with `sample_words` words and `planes` bit planes -- the library's own partition code
+ * (reo_pairs2.cu), replayed on the host.  mode: 0 = the shape the library would choose, 1 = force one-sided.
+ * out: triples (row tile, column tile, 1 = the pairs update their row genes | 2 = ... their column genes) in the panel
+ * coordinates of that shape; *nsym_tiles / *ntr / *ntc describe it.  Returns the number of triples (may exceed cap). */
+long long reo_debug_pair_plan(int64_t r, int64_t ncols, int32_t sample_words, int32_t planes, int32_t rank, int32_t world,
+                              int32_t mode, int32_t* out, int64_t cap, int32_t* nsym_tiles, int32_t* ntr, int32_t* ntc) {
+    if (r < 1 || ncols < 1 || ncols > r || world < 1 || rank < 0 || rank >= world || sample_words < 1 || planes < 2) return -1;
+    ReoPair2Params p;
+    memset(&p, 0, sizeof(p));
+    p.T = reo_pairs2_block_edge(sample_words, planes);
+    p.rank = rank; p.world = world; p.W = sample_words; p.NP = planes;
+    const int NT = (int)((r + REO_TILE - 1) / REO_TILE);
+    const int tc = (int)((ncols + REO_TILE - 1) / REO_TILE);
+    if (ncols == r && mode == 0) { p.ntr = p.ntc = p.nsym = NT; }
+    else if (mode == 0 && sym_worth(ncols, r)) {
+        const int nsymp = (tc + p.T - 1) / p.T * p.T;
+        p.ntr = nsymp + (int)((r - ncols + REO_TILE - 1) / REO_TILE); p.ntc = p.nsym = tc;
+    } else { p.ntr = NT; p.ntc = tc; p.nsym = 0; }
+    if (nsym_tiles) *nsym_tiles = p.nsym;
+    if (ntr) *ntr = p.ntr;
+    if (ntc) *ntc = p.ntc;
+    return reo_pairs2_plan(p, out, cap);
+}
+
 /* Per-level iteration log of the last reo_identify_degs (the reference's @info lines, src:418-420, 432-435). */
 int reo_iter_log(reo_handle_t h, int32_t k, int32_t* iters_done, int32_t* converged, int32_t* n_deg, int32_t* n_ref,
                  int32_t cap) {

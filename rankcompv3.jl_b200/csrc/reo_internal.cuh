@@ -112,6 +112,8 @@ struct ReoPair2Params {
 };
 cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st);
 int reo_pairs2_block_edge(int W, int NP);   // T for a staged matrix
+// host replay of a rank's tile pairs: (row tile, column tile, 1 = updates row genes | 2 = updates column genes) triples
+long long reo_pairs2_plan(ReoPair2Params p, int32_t* out, long long cap);
 
 // kernels / launchers implemented in the .cu files
 struct ReoDev;  // per-device state (reo_api.cu)

@@ -66,7 +66,7 @@ __device__ __forceinline__ void p2_consumer_bar() { asm volatile("bar.sync 1, %0
 // work item n of this rank -> block (bi, bj) and row part `sub` of the block; false: nothing to do for this index.
 // Items are numbered supertile by supertile (L2 locality of the CTAs in flight) and dealt round-robin to the ranks:
 // every rank gets the same number of items of every supertile (+-1), whatever the shape of the tile space.
-__device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int n, int& bi, int& bj, int& sub) {
+__host__ __device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int n, int& bi, int& bj, int& sub) {
     const long long g = (long long)n * p.world + p.rank;
     const int per_sup = p.SS * p.SS * p.RS;
     const long long s = g / per_sup;
@@ -89,6 +89,48 @@ __device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int n, int& b
     bi = p.NBs + (int)(s2 / p.Mc) * p.SS + di;
     bj = (int)(s2 % p.Mc) * p.SS + dj;
     return bi < p.NBr && bj < p.NBc;
+}
+
+// Tile pairs (64 rows x 128 columns) of work item n, in processing order: f(I, B0, Ja, J0, hasB, flags, last) with
+// I = row tile, B0 / J0 = first row / column tile of the item's block, Ja = first column tile of the pair, hasB = the
+// second column tile exists, flags = P2F_ROW0 | COL0 | ROW1 | COL1 (which genes the pairs update), last = last pair of
+// the item.  Used by the kernel's producer warp AND by reo_pairs2_plan (host, tests): one enumeration, one truth.
+template <class F>
+__host__ __device__ __forceinline__ void p2_for_each_tile_pair(const ReoPair2Params& p, int n, F&& f) {
+    int bi, bj, sub;
+    if (!p2_decode(p, n, bi, bj, sub)) return;
+    const int T = p.T;
+    const bool symrow = bi < p.NBs;
+    const int TI = T / p.RS;                       // row tiles of one item
+    const int B0 = bi * T, J0 = bj * T;            // first row / column tile of the block
+    const int I0 = B0 + sub * TI;
+    const int Ilim = symrow ? p.nsym : p.ntr;
+    const int Iend = I0 + TI < Ilim ? I0 + TI : Ilim;
+    const int Jend = J0 + T < p.ntc ? J0 + T : p.ntc;
+    const int jphi = (Jend + 1) >> 1;
+    int left = 0;                                  // tile pairs of this item
+    for (int I = I0; I < Iend; ++I) {
+        int jplo = J0 >> 1;
+        if (symrow && (I >> 1) > jplo) jplo = I >> 1;
+        if (jphi > jplo) left += jphi - jplo;
+    }
+    for (int I = I0; I < Iend; ++I) {
+        int jplo = J0 >> 1;
+        if (symrow && (I >> 1) > jplo) jplo = I >> 1;
+        for (int jp = jplo; jp < jphi; ++jp) {
+            const int Ja = 2 * jp, Jb = Ja + 1;
+            const bool hasB = Jb < p.ntc;
+            int tf = 0;
+            if (symrow) {
+                if (Ja >= I) tf |= P2F_ROW0 | (Ja > I ? P2F_COL0 : 0);
+                if (hasB && Jb >= I) tf |= P2F_ROW1 | (Jb > I ? P2F_COL1 : 0);
+            } else {
+                tf |= P2F_ROW0 | (hasB ? P2F_ROW1 : 0);
+            }
+            --left;
+            f(I, B0, Ja, J0, hasB, tf, left == 0);
+        }
+    }
 }
 
 // NPT > 0: planes known at compile time (fully unrolled chain); NPT == 0: runtime p.NP.
@@ -161,41 +203,10 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
         };
         int slot = 0;
         uint32_t ephase = 1u;       // parity that means "slot is free": passes at once on the first round
-        const int nsymp = p.NBs * T;
         for (;;) {
             const int n = (int)atomicAdd(p.counter, 1u);
             if (n >= p.nitems) break;
-            int bi, bj, sub;
-            if (!p2_decode(p, n, bi, bj, sub)) continue;
-            const bool symrow = bi < p.NBs;
-            const int TI = T / p.RS;                       // row tiles of one item
-            const int B0 = bi * T, J0 = bj * T;            // first row / column tile of the block
-            const int I0 = B0 + sub * TI;
-            const int Iend = symrow ? min(I0 + TI, p.nsym) : min(I0 + TI, p.ntr);
-            const int Jend = min(J0 + T, p.ntc);
-            const int jphi = (Jend + 1) >> 1;
-            int left = 0;            // tile pairs (64 x 128) of this item
-            for (int I = I0; I < Iend; ++I) {
-                int jplo = J0 >> 1;
-                if (symrow) jplo = max(jplo, I >> 1);
-                left += max(0, jphi - jplo);
-            }
-            if (left == 0) continue;
-            (void)nsymp;
-            for (int I = I0; I < Iend; ++I) {
-                int jplo = J0 >> 1;
-                if (symrow) jplo = max(jplo, I >> 1);
-                for (int jp = jplo; jp < jphi; ++jp) {
-                    const int Ja = 2 * jp, Jb = Ja + 1;
-                    const bool hasB = Jb < p.ntc;
-                    int tf = 0;
-                    if (symrow) {
-                        if (Ja >= I) tf |= P2F_ROW0 | (Ja > I ? P2F_COL0 : 0);
-                        if (hasB && Jb >= I) tf |= P2F_ROW1 | (Jb > I ? P2F_COL1 : 0);
-                    } else {
-                        tf |= P2F_ROW0 | (hasB ? P2F_ROW1 : 0);
-                    }
-                    --left;
+            p2_for_each_tile_pair(p, n, [&](int I, int B0, int Ja, int J0, bool hasB, int tf, bool last_pair) {
                     const uint32_t* rbase = p.row_planes + (size_t)I * tile_stride;
                     const uint32_t* cbase = p.col_planes + (size_t)Ja * tile_stride;
                     for (int ch = 0; ch < nchunks; ++ch) {
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                         A->kb = (p.WA >= w0 && p.WA < w0 + nw) ? p.WA - w0 : -1;
                         A->il = I - B0; A->jl = Ja - J0; A->rbase = B0 * REO_TILE; A->cbase = J0 * REO_TILE;
                         A->flags = tf | (first ? P2F_FIRST_J : 0) | (last ? P2F_LAST_J : 0) |
-                                   ((last && left == 0) ? P2F_LAST_ITEM : 0);
+                                   ((last && last_pair) ? P2F_LAST_ITEM : 0);
                         uint32_t bytes = (uint32_t)nw * op_bytes * (hasB ? 3u : 2u);
                         // gene ids travel with the first stage of a tile pair (orientation of the tie coin) and, together
                         // with the signs, with its last stage (table update): consumers keep none of them in registers
@@ -239,8 +250,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                         }
                         if (++slot == NS) { slot = 0; ephase ^= 1u; }
                     }
-                }
-            }
+            });
         }
         // no more work: one terminating stage
         mbar_wait_parked(&empty[slot], ephase);
@@ -561,9 +571,8 @@ static cudaError_t launch_p2_np(const ReoPair2Params& p, size_t smem, int num_sm
     return launch_p2<NPT, P2_WIDE>(p, smem, num_sms, st);
 }
 
-// Fills the geometry (blocks, supertiles, ring) from ntr / ntc / nsym / T / W / NP / rank / world and launches.
-cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st) {
-    if (p.ntr <= 0 || p.ntc <= 0) return cudaSuccess;
+// Geometry of a launch (blocks, supertiles, items of this rank) from ntr / ntc / nsym / T / W / NP / rank / world.
+static void p2_geometry(ReoPair2Params& p) {
     const int T = p.T;
     p.NBs = (p.nsym + T - 1) / T;
     const int nsymp = p.NBs * T;
@@ -597,7 +606,33 @@ cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st) {
     const long long total_items = p.NSUP * p.SS * p.SS * p.RS;
     const long long mine = total_items > p.rank ? (total_items - p.rank + p.world - 1) / p.world : 0;
     p.nitems = (int)std::min<long long>(mine, 0x7fffffff);
+}
+
+// Host-side replay of what the producer warps of rank p.rank will do: every (row tile, column tile, update flags) this
+// rank evaluates, through the SAME p2_decode / p2_for_each_tile_pair as the kernel.  out: 3 ints per half tile pair.
+// For the CPU tests of the multi-rank partition (no GPU needed).
+long long reo_pairs2_plan(ReoPair2Params p, int32_t* out, long long cap) {
+    if (p.ntr <= 0 || p.ntc <= 0) return 0;
+    p2_geometry(p);
+    long long n_out = 0;
+    for (int n = 0; n < p.nitems; ++n)
+        p2_for_each_tile_pair(p, n, [&](int I, int, int Ja, int, bool hasB, int tf, bool) {
+            for (int half = 0; half < (hasB ? 2 : 1); ++half) {
+                const int rowf = half ? P2F_ROW1 : P2F_ROW0, colf = half ? P2F_COL1 : P2F_COL0;
+                if (!(tf & (rowf | colf))) continue;
+                if (out && n_out < cap) { out[3 * n_out] = I; out[3 * n_out + 1] = Ja + half; out[3 * n_out + 2] = ((tf & rowf) ? 1 : 0) | ((tf & colf) ? 2 : 0); }
+                ++n_out;
+            }
+        });
+    return n_out;
+}
+
+// Fills the geometry and the ring, and launches.
+cudaError_t reo_launch_pairs2(ReoPair2Params p, int num_sms, cudaStream_t st) {
+    if (p.ntr <= 0 || p.ntc <= 0) return cudaSuccess;
+    p2_geometry(p);
     if (p.nitems <= 0) return cudaSuccess;
+    const int T = p.T;
     // lookup tables
     const int sza = p.nA + p.padA + 1, szb = p.nB + p.padB + 1;
     p.lutSZA = sza; p.lutSZB = szb;

@@ -1,33 +1,41 @@
-"""Row-tile sharding across one process per GPU.  The pair kernel's work is independent per
-gene row, so gene-row tiles are split into `world` contiguous, equal-sized slices (the last ranks may own
-fewer or no real tiles) and the per-gene Int32 tables are all-gathered; K3-K6 then run replicated on every
-rank (deterministic FP64 -> identical masks, one collective per evaluation, no mask broadcast)."""
+"""One process per GPU.  The pair kernel's tile space -- symmetric sweep or rows x columns -- is cut into work
+items that are dealt round-robin to the ranks (every world-th item, scrambled inside each supertile: csrc/reo_pairs2.cu);
+every rank therefore holds partial sums for ALL genes, the per-gene Int32 tables are summed over the ranks (NCCL
+all-reduce inside the library, or any all-gather handed in through reo_set_collective followed by a local sum) and K3-K6
+run replicated on every rank (deterministic FP64 -> identical masks, one collective per evaluation, no mask broadcast).
+K1 is sharded by sample words when the matrix is large.  Nothing here re-implements the partition: `pair_plan` asks the
+library itself (reo_debug_pair_plan, host code, no GPU needed) which tile pairs a rank evaluates."""
 from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
 
 TILE = 64
 
 
-def shard_plan(n_tiles: int, world: int):
-    """(tiles_per_rank, [(t0, t1) per rank]) -- mirrors launch_tables() in csrc/reo_api.cu."""
-    tpr = -(-n_tiles // world)
-    return tpr, [(min(n_tiles, q * tpr), min(n_tiles, (q + 1) * tpr)) for q in range(world)]
+def pair_plan(r: int, ncols: int, sample_words: int, planes: int, rank: int, world: int, one_sided: bool = False):
+    """The library's own partition for a table build over `ncols` of `r` genes: (triples, nsym_tiles, ntr, ntc) with
+    triples[:, 0] = row tile, [:, 1] = column tile (panel coordinates), [:, 2] = 1 (pairs update their row genes) |
+    2 (... their column genes).  nsym_tiles > 0: the first nsym_tiles row tiles are the column panel itself."""
+    lib = L.load()
+    ns, ntr, ntc = C.c_int32(), C.c_int32(), C.c_int32()
+    args = (int(r), int(ncols), int(sample_words), int(planes), int(rank), int(world), 1 if one_sided else 0)
+    n = lib.reo_debug_pair_plan(*args, None, 0, C.byref(ns), C.byref(ntr), C.byref(ntc))
+    if n < 0:
+        raise ValueError("reo_debug_pair_plan: bad argument")
+    out = np.zeros((max(int(n), 1), 3), dtype=np.int32)
+    lib.reo_debug_pair_plan(*args, out.ctypes.data, int(n), C.byref(ns), C.byref(ntr), C.byref(ntc))
+    return out[:int(n)], ns.value, ntr.value, ntc.value
 
 
 def word_shard_plan(n_words: int, world: int):
-    """K1 sharding: (words_per_rank, [(w_lo, w_hi) per rank]) over the staged sample words -- mirrors do_stage() in
-    csrc/reo_api.cu.  Ranks past the last word stage nothing; the all-gathered blocks are padded to words_per_rank."""
+    """K1 sharding: (words_per_rank, [(w_lo, w_hi) per rank]) over the staged sample words (do_stage() in csrc/reo_api.cu).
+    Ranks past the last word stage nothing; the all-gathered blocks are padded to words_per_rank."""
     wq = -(-n_words // world)
     return wq, [(min(n_words, q * wq), min(n_words, (q + 1) * wq)) for q in range(world)]
-
-
-def k1_is_sharded(r: int, c: int, world: int, data_on_device: bool) -> bool:
-    """Staging is sharded from 2^24 values resident in HBM, from 2^20 values for host input (mirrors do_stage())."""
-    return world > 1 and r * c >= (1 << 24 if data_on_device else 1 << 20)
-
-
-def table_slice_bytes(n_tiles: int, world: int) -> int:
-    tpr, _ = shard_plan(n_tiles, world)
-    return tpr * TILE * 9 * 4
 
 
 class DevBuf:
@@ -38,7 +46,8 @@ class DevBuf:
 
 
 def make_torch_allgather(rank: int, world: int, group=None):
-    """In-place all-gather callback for Reo.set_collective, over torch.distributed (NCCL on GPUs)."""
+    """In-place all-gather callback for Reo.set_collective, over torch.distributed (NCCL on GPUs): the library gathers
+    the ranks' partial tables with it and sums them itself."""
     import torch
     import torch.distributed as dist
 
@@ -51,22 +60,9 @@ def make_torch_allgather(rank: int, world: int, group=None):
     return allgather
 
 
-def allgather_rows_cpu(local_rows, rank: int, world: int, n_tiles: int, group=None):
-    """Host-side twin of the table exchange (gloo): every rank contributes the [tpr*64, 9] Int32 slice of
-    the tiles it owns and receives the full table.  Used by the CPU tests of the N>1 path."""
-    import torch
-    import torch.distributed as dist
-    tpr, _ = shard_plan(n_tiles, world)
-    mine = torch.zeros((tpr * TILE, 9), dtype=torch.int32)
-    mine[: local_rows.shape[0]] = torch.as_tensor(local_rows, dtype=torch.int32)
-    full = torch.zeros((world * tpr * TILE, 9), dtype=torch.int32)
-    dist.all_gather_into_tensor(full, mine, group=group)
-    return full.numpy()
-
-
 def init_nccl_in_library(handle, rank: int, world: int, group=None):
-    """One process per GPU: create the library's own NCCL communicator (tables are then all-gathered on the
-    library's stream with no host round trip).  The 128-byte unique id travels over torch.distributed."""
+    """One process per GPU: create the library's own NCCL communicator (tables are then summed on the library's stream
+    with no host round trip).  The 128-byte unique id travels over torch.distributed."""
     import torch.distributed as dist
     from . import api
     box = [api.nccl_unique_id() if rank == 0 else None]

@@ -73,14 +73,32 @@ def test_synth_shapes(pkg):
     assert m.sum() == 50 and not (m & de).any()
 
 
-def test_shard_plan(pkg):
+def test_pair_plan_covers_every_tile_pair_once(pkg):
+    """The library's partition (reo_debug_pair_plan = csrc/reo_pairs2.cu on the host): over all ranks every needed
+    (row tile, column tile) is evaluated exactly once, in every shape, at any rank count."""
     from importlib import import_module
     dist = import_module(pkg.__name__ + ".dist")
-    for nt, world in ((469, 8), (5, 8), (313, 2), (1, 1)):
-        tpr, ranges = dist.shard_plan(nt, world)
-        assert tpr == -(-nt // world) and len(ranges) == world
-        covered = [t for (a, b) in ranges for t in range(a, b)]
-        assert covered == list(range(nt))
+    for r, ncols, W, NP in ((30000, 30000, 625, 8), (20000, 3000, 7, 13), (20000, 15000, 7, 13), (700, 700, 1, 10), (130, 70, 3, 5)):
+        for world in (1, 3, 8):
+            seen = {}
+            sizes = []
+            for rank in range(world):
+                trip, nsym, ntr, ntc = dist.pair_plan(r, ncols, W, NP, rank, world)
+                sizes.append(len(trip))
+                for I, J, fl in trip:
+                    assert (int(I), int(J)) not in seen
+                    seen[(int(I), int(J))] = int(fl)
+            nt = -(-r // 64)
+            tc = -(-ncols // 64)
+            if nsym == 0:
+                want = {(i, j): 1 for i in range(nt) for j in range(tc)}
+            else:
+                want = {(i, j): (3 if j > i else 1) for i in range(nsym) for j in range(i, nsym)}
+                n_rest = -(-(r - ncols) // 64)
+                want.update({(i, j): 1 for i in range(ntr - n_rest, ntr) for j in range(ntc)})
+            assert seen == want, (r, ncols, world)
+            if sum(sizes) >= 4000:   # balance matters (and is only meaningful) on large tile spaces; edge half pairs count 1
+                assert max(sizes) - min(sizes) <= 0.06 * sum(sizes) / world, (r, ncols, world, sizes)
 
 
 def test_pinned_output_pool_recycles_and_caps(pkg, monkeypatch):
