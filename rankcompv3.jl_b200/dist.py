@@ -31,13 +31,6 @@ def pair_plan(r: int, ncols: int, sample_words: int, planes: int, rank: int, wor
     return out[:int(n)], ns.value, ntr.value, ntc.value
 
 
-def word_shard_plan(n_words: int, world: int):
-    """K1 sharding: (words_per_rank, [(w_lo, w_hi) per rank]) over the staged sample words (do_stage() in csrc/reo_api.cu).
-    Ranks past the last word stage nothing; the all-gathered blocks are padded to words_per_rank."""
-    wq = -(-n_words // world)
-    return wq, [(min(n_words, q * wq), min(n_words, (q + 1) * wq)) for q in range(world)]
-
-
 class DevBuf:
     """A raw device pointer exposed through __cuda_array_interface__ so torch can wrap it without a copy."""
 

@@ -137,15 +137,3 @@ def test_pinned_output_pool_recycles_and_caps(pkg, monkeypatch):
     assert st.freed == [p0] and api._pinned_pooled == 0
 
 
-def test_word_shard_plan_covers_every_word_once(pkg):
-    from importlib import import_module
-    d = import_module(pkg.__name__ + ".dist")
-    for W in (1, 2, 7, 8, 9, 250, 625):
-        for world in (1, 2, 3, 4, 8):
-            wq, ranges = d.word_shard_plan(W, world)
-            assert wq * world >= W and len(ranges) == world
-            seen = [w for lo, hi in ranges for w in range(lo, hi)]
-            assert seen == list(range(W))                   # disjoint, ordered, complete; empty ranks allowed
-            assert all(hi - lo <= wq for lo, hi in ranges)
-    assert d.k1_is_sharded(30000, 20000, 8, True) and not d.k1_is_sharded(20000, 200, 8, True)
-    assert d.k1_is_sharded(20000, 200, 8, False) and not d.k1_is_sharded(20000, 200, 1, False)
