@@ -2,8 +2,9 @@
 # libreo_cuda.so (include/reo.h) through ccall.  Everything else in RankCompV3.jl stays as it is.
 #
 # NOTE: Julia is not installed in the build image, so this file is delivered as the binding a maintainer
-# would add; the identical ABI is exercised by the Python ctypes harness (rankcompv3.jl_b200/api.py) and
-# by tests/test_gpu_parity.py.
+# would add; the identical ABI is exercised by the Python ctypes harness (rankcompv3.jl_b200/api.py), by the plain-C
+# caller examples/reo_driver.c and by tests/test_gpu_parity.py.  The input matrix is ordinary (pageable) Julia memory:
+# the library pipelines it through pinned bounce buffers (bench.py reports that path as e2e.pageable).
 #
 # Usage inside the package:   include("reo_ccall.jl")   after the original definition of identify_degs,
 # or replace the body of identify_degs with `return identify_degs_cuda(...)`.
@@ -28,6 +29,20 @@ struct ReoStats
     ms_wall::Float64
     pair_launches::Int32
     kernel_launches::Int32
+    ordered_triples::Int64
+end
+
+const REO_OUT_PINNED = UInt32(2)
+
+# Page-locked output block from reo_host_alloc: the library DMAs the results straight into it (REO_OUT_PINNED); the
+# finalizer hands the block back with reo_host_free when the Julia array is collected.
+function reo_pinned_array(::Type{T}, dims::Integer...) where {T}
+    n = max(prod(dims) * sizeof(T), 1)
+    p = ccall((:reo_host_alloc, LIBREO), Ptr{Cvoid}, (Csize_t,), n)
+    p == C_NULL && throw(OutOfMemoryError())
+    a = unsafe_wrap(Array, Ptr{T}(p), dims; own = false)
+    finalizer(x -> ccall((:reo_host_free, LIBREO), Cvoid, (Ptr{Cvoid},), pointer(x)), a)
+    return a
 end
 
 reo_dtype(::Type{Int64}) = 0; reo_dtype(::Type{Float64}) = 1
@@ -73,9 +88,9 @@ function identify_degs_cuda(data::AbstractMatrix, group::AbstractVector, gene_na
     gsi1 = [count(==(l), group) for l in glev]; gsi2 = c .- gsi1
     thr = Matrix{Int32}(get_major_reo_lower_count.(Matrix(hcat(gsi1, gsi2)'), pval_reo))   # 2 x gnum
     K = gnum == 2 ? 1 : gnum
-    result = Array{Float64,3}(undef, r, 15, K)
-    updown = Matrix{Int8}(undef, r, K)
-    final_ref = Matrix{UInt8}(undef, r, K)
+    result = reo_pinned_array(Float64, r, 15, K)                   # page-locked: results are DMA-ed straight into them
+    updown = reo_pinned_array(Int8, r, K)
+    final_ref = reo_pinned_array(UInt8, r, K)
     iters = Vector{Int32}(undef, K)
     stats = Ref{ReoStats}()
     ref = Vector{UInt8}(ref_gene)
@@ -84,14 +99,25 @@ function identify_degs_cuda(data::AbstractMatrix, group::AbstractVector, gene_na
               (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64, Int64, Ptr{Int32}, Int32, Ptr{Int32}, Float64, Float64, Float64,
                Ptr{UInt8}, Int32, Int32, UInt32, Ptr{Float64}, Ptr{Int8}, Ptr{UInt8}, Ptr{Int32}, Ref{ReoStats}),
               handle.ptr, mat, reo_dtype(T), r, c, r, gid, gnum, thr, pval_reo, pval_deg, padj_deg,
-              ref, n_iter, n_conv, 0, result, updown, final_ref, iters, stats)
+              ref, n_iter, n_conv, REO_OUT_PINNED, result, updown, final_ref, iters, stats)
     end
     rc == REO_OK || reo_throw(handle, rc)
-    st = stats[]
-    for e in 1:min(st.iters_done, REO_MAX_ITER_LOG)                 # the reference's @info lines, src:418
-        @info "INFO: iteration $(e-1),  # DEGs $(st.n_deg[e]), # non-DEGs $(r - st.n_deg[e])"
+    # the reference's log lines, per level k (src:418-420, 432-435), from the library's per-level iteration log
+    n_deg = Vector{Int32}(undef, REO_MAX_ITER_LOG); n_ref = similar(n_deg)
+    for k in 1:K
+        it = Ref{Int32}(0); cv = Ref{Int32}(0)
+        ccall((:reo_iter_log, LIBREO), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}, Ptr{Int32}, Ptr{Int32}, Int32),
+              handle.ptr, k - 1, it, cv, n_deg, n_ref, REO_MAX_ITER_LOG)
+        for e in 1:min(it[], REO_MAX_ITER_LOG)
+            @info "INFO: iteration $(e-1),  # DEGs $(n_deg[e]), # non-DEGs $(r - n_deg[e])"        # src:418
+        end
+        cv[] == 1 && @info "INFO: Convergence threshold is reached"                                # src:420
+        if gnum == 2                                                                               # src:431-435
+            @info "INFO: The results of differentially expressed genes in the iteration process of $(glev[1]) vs $(glev[2]) were output."
+        else
+            @info "INFO: The results of differentially expressed genes in the iteration process of $(glev[k]) vs other were output."
+        end
     end
-    st.converged == 1 && @info "INFO: Convergence threshold is reached"   # src:420
     res = gene_names                                               # src:394
     for k in 1:K
         ud = String.(gene_names); ud .= "no change"

@@ -355,6 +355,31 @@ def test_single_process_multi_gpu_matches_single_gpu(reo, pkg, oracle, coracle):
             os.environ.pop("REO_K1_SHARD_MIN", None)
 
 
+def test_iter_log_per_level_and_input_memory_kinds(reo, pkg, oracle, coracle):
+    """Three levels: reo_iter_log returns every level's log (what the Julia shim prints, src:418-420, 432-435), and the
+    result does not depend on where the input lives: pageable numpy memory (pinned bounce pipeline), page-locked
+    memory (direct DMA) or HBM."""
+    import torch
+    data, group = small_case(21, 400, 12, 20, n3=17)
+    levels, gid = oracle.group_levels(group)
+    ref = np.arange(400) % 3 == 0
+    thr = coracle.thresholds_for(gid, 3, 0.01)
+    want = coracle.identify_degs(data, gid, 3, thr, 1.0, 0.05, ref, 128, 5, seed=7)
+    out = reo.identify_degs(data, gid, 3, ref, 0.01, 1.0, 0.05, 128, 5)                      # pageable
+    check_full(out, want)
+    for k in range(3):
+        log = reo.iter_log(k)
+        assert log["iters_done"] == want["iters"][k] == len(log["n_deg"])
+        assert log["n_deg"] == [int(v) for v in want["deg_log"][k][:log["iters_done"]]]
+    pinned = torch.from_numpy(np.ascontiguousarray(data.T)).pin_memory()                     # [c, r] == r x c column-major
+    out_p = reo.identify_degs(pinned.numpy().T, gid, 3, ref, 0.01, 1.0, 0.05, 128, 5)
+    dev = pinned.cuda()
+    dm = pkg.DeviceMatrix(dev.data_ptr(), pkg._lib.REO_I64, 400, data.shape[1], 400, keepalive=dev)
+    out_d = reo.identify_degs(dm, gid, 3, ref, 0.01, 1.0, 0.05, 128, 5)
+    for o in (out_p, out_d):
+        assert np.array_equal(o.result, out.result) and np.array_equal(o.updown, out.updown)
+
+
 def test_subset_and_detect_more_than_65535_cells(reo):
     """gridDim.y is capped at 65535: the kernels next to the path stride over the cell dimension."""
     rng = np.random.default_rng(3)
