@@ -380,6 +380,23 @@ def test_iter_log_per_level_and_input_memory_kinds(reo, pkg, oracle, coracle):
         assert np.array_equal(o.result, out.result) and np.array_equal(o.updown, out.updown)
 
 
+def test_more_than_65535_samples_per_group_wide_counters(reo, oracle, coracle):
+    """> 65 535 sample slots in a group: the pair kernel's packed 16-bit counters do not fit and the 32-bit variant runs."""
+    rng = np.random.default_rng(9)
+    r, n1, n2 = 70, 66000, 300
+    mu = np.exp(rng.normal(1.0, 1.0, r))
+    data = rng.poisson(mu[:, None] * np.ones((1, n1 + n2))).astype(np.int32)
+    data[:10, n1:] += 2
+    gid = np.array([0] * n1 + [1] * n2, dtype=np.int32)
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    mask = np.arange(r) % 5 != 0
+    reo.stage(data, gid, 2)
+    tab, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)
+    assert np.array_equal(reo.tables(0, mask, thresholds=thr), tab)
+    tab_all, _ = coracle.block_tables(data, gid, 2, thr, np.arange(r), seed=7)
+    assert np.array_equal(reo.tables(0, np.ones(r, bool), thresholds=thr), tab_all)
+
+
 def test_subset_and_detect_more_than_65535_cells(reo):
     """gridDim.y is capped at 65535: the kernels next to the path stride over the cell dimension."""
     rng = np.random.default_rng(3)
