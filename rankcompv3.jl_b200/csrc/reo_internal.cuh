@@ -24,6 +24,11 @@ __host__ __device__ __forceinline__ uint32_t reo_mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
     return x;
 }
+// bit 31 of reo_mix32(x): the mixer's last xor-shift (x ^= x >> 16) cannot change the top bit
+__host__ __device__ __forceinline__ uint32_t reo_mix32_top(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu;
+    return x >> 31;
+}
 __host__ __device__ __forceinline__ uint32_t reo_coin_u(uint32_t seed_lo, uint32_t seed_hi, uint32_t gene,
                                                         uint32_t sample) {
     uint32_t h = reo_mix32(seed_lo ^ (gene * 0x9E3779B1u));

@@ -481,14 +481,14 @@ bitplanes_kernel(const RT* __restrict__ ranks, int64_t rpad, int64_t r,
         const int myp = lane % FW, myk = lane / FW;     // after the transpose: this lane's plane and gene in the group
         const uint32_t* trow = tile + lane * LDW;
 #pragma unroll 2
-        for (int grp = 0; grp < GW / GPW; ++grp) {
+        for (int grp = 0; grp < GW / GPW; ++grp) {   // (full unrolling measured slower: 2.64 vs 2.47 ms of staging on 30k x 20k)
             uint32_t x = 0u;
 #pragma unroll
             for (int k = 0; k < GPW; ++k) {
                 const int gi = wid * GW + grp * GPW + k;                      // gene within the CTA
                 uint32_t rk = trow[gi / PER];
                 if (PER == 2) rk = (gi & 1) ? (rk >> 16) : (rk & 0xffffu);
-                const uint32_t coin = reo_mix32(ghash[gi] + sterm) >> 31;
+                const uint32_t coin = reo_mix32_top(ghash[gi] + sterm);
                 x |= ((rk << 1) | coin) << (k * FW);
             }
             x = warp_transpose32(x, lane) & slotmask;                        // pad slots contribute nothing
