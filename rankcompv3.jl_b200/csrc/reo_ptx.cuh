@@ -48,8 +48,30 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
         : "memory");
     return ok != 0u;
 }
+// non-blocking probe of a phase: returns at once (try_wait may park the thread for a system-dependent time, and a parked
+// thread was measured to wake up late when the phase is completed by the byte count of a bulk copy)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+#ifndef REO_PARK_NS
+#define REO_PARK_NS 1000000u
+#endif
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait_hint(bar, parity, 1000000u)) { }
+#if defined(REO_WAIT_TEST)
+    while (!mbar_test_wait(bar, parity)) { if (REO_WAIT_TEST > 0) __nanosleep(REO_WAIT_TEST); }
+#else
+    while (!mbar_try_wait_hint(bar, parity, REO_PARK_NS)) { }
+#endif
 }
 // global -> shared bulk copy (UBLKCP), completion counted in bytes on `bar`; 16-byte aligned addresses and size
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -26,6 +26,11 @@ else:
 ref = pkg.synth.reference_mask(is_de, n_ref) if n_ref > 0 else np.ones(r, dtype=bool)
 _, gid = pkg.api.group_levels(group)
 h = pkg.Reo(0, seed=pkg.synth.TIE_SEED)
+if os.environ.get("REO_FAKE_WORLD"):
+    # timing study on ONE GPU of what rank 0 of a `world`-rank job does: the pair-tile space is partitioned for `world`
+    # ranks and the (dummy) collective gathers nothing, so the tables are partial and the RESULTS ARE WRONG -- only the
+    # launch times mean anything
+    h.set_collective(0, int(os.environ["REO_FAKE_WORLD"]), lambda ptr, nbytes: None)
 dm = pkg.DeviceMatrix(t.data_ptr(), pkg._lib.REO_I64, r, n1 + n2, r, keepalive=t)
 for i in range(reps):
     torch.cuda.synchronize()
