@@ -32,6 +32,8 @@ def lib():
         L.reo_oracle_num_threads.restype = C.c_int
         L.reo_oracle_set_threads.restype = None
         L.reo_oracle_set_threads.argtypes = [C.c_int]
+        L.reo_oracle_set_input_f32.restype = None
+        L.reo_oracle_set_input_f32.argtypes = [C.c_int]
         L.reo_oracle_set_coin_mode.restype = None
         L.reo_oracle_set_coin_mode.argtypes = [C.c_int]
         L.reo_oracle_threshold.restype = C.c_int
@@ -67,8 +69,11 @@ def _p(a):
 
 
 def _colmajor_f64(data):
-    """Julia layout: column-major r x c Float64."""
-    return np.asfortranarray(np.asarray(data, dtype=np.float64))
+    """Julia layout: column-major r x c Float64.  A float32 matrix switches the oracle to Float32 differences (the
+    reference evaluates abs(x - y) in the matrix' own element type, src:72); any other dtype switches it back."""
+    a = np.asarray(data)
+    lib().reo_oracle_set_input_f32(1 if a.dtype == np.float32 else 0)
+    return np.asfortranarray(a, dtype=np.float64)
 
 
 def num_threads() -> int:

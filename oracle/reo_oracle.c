@@ -202,6 +202,10 @@ typedef struct {
  *   0  coin(i,j,s) = u(i,s) ^ u(j,s) ^ [i<j]          -- G bits of entropy per sample, free in the bit-sliced kernel
  *   1  coin(i,j,s) = h(seed, min(i,j), max(i,j), s)    -- an independent fair coin per (unordered pair, sample), which is
  *                     what the reference's rand(Bool) (src:73) draws; mirrored for (j,i) as src:385-386 requires */
+/* Element type of the caller's matrix: Julia evaluates abs(x - y) in the matrix' own type before comparing with the
+ * Float64 literal 0.1 (src:72), so for Matrix{Float32} the difference is rounded to Float32 first. */
+static int g_input_f32 = 0;
+void reo_oracle_set_input_f32(int on) { g_input_f32 = on; }
 static int g_coin_mode = 0;
 void reo_oracle_set_coin_mode(int mode) { g_coin_mode = mode; }
 static inline uint32_t pair_coin(uint64_t seed, uint32_t lo, uint32_t hi, uint32_t s) {
@@ -220,7 +224,7 @@ static inline void pair_counts(const reo_ctx* x, int64_t i, int64_t j, int64_t* 
     const uint8_t o = (uint8_t)(i < j);
     for (int g = 0; g < x->gnum; ++g) nre[g] = 0;
     for (int64_t s = 0; s < x->c; ++s) {
-        double d = a[s] - b[s];
+        double d = g_input_f32 ? (double)((float)a[s] - (float)b[s]) : a[s] - b[s];
         int gt;
         if (fabs(d) < 0.1) {                         /* src:72-73, deterministic coin */
             if (g_coin_mode == 0) gt = ua[s] ^ ub[s] ^ o;

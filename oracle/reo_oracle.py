@@ -357,8 +357,10 @@ def greater_counts(data, gid, gnum, rows, cols, seed=0, u=None):
     cols = np.asarray(cols, dtype=np.int64)
     if u is None:
         u = coin_bits(seed, r, c)
-    X = data[rows].astype(np.float64)
-    Y = data[cols].astype(np.float64)
+    # Matrix{Float32} input: Julia subtracts in Float32 and only then compares with the Float64 literal 0.1 (src:72)
+    f32 = data.dtype == np.float32
+    X = data[rows] if f32 else data[rows].astype(np.float64)
+    Y = data[cols] if f32 else data[cols].astype(np.float64)
     uX = u[rows]
     uY = u[cols]
     lt_idx = (rows[:, None] < cols[None, :])
@@ -368,7 +370,7 @@ def greater_counts(data, gid, gnum, rows, cols, seed=0, u=None):
         for s in sel:
             x = X[:, s][:, None]
             y = Y[:, s][None, :]
-            tie = np.abs(x - y) < 0.1
+            tie = np.abs(x - y).astype(np.float64) < 0.1   # (x - y) is rounded to Float32 first when the input is
             coin = (uX[:, s][:, None] ^ uY[:, s][None, :]) ^ lt_idx
             out[k] += np.where(tie, coin.astype(bool), x > y)
     return out

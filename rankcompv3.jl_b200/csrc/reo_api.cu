@@ -326,7 +326,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
              int32_t gnum, uint32_t flags) {
     ReoDev& D = h->devs[0];
     ReoStaged& S = D.S;
-    S.valid = false; S.flt = false;
+    S.valid = false; S.flt = false; S.flt_f32 = false;
     const size_t es = dtype_size(dtype);
     if (!data || !group_id || es == 0 || r < 1 || c < 1 || ld < r) return fail(h, REO_ERR_ARG, "reo_stage: bad argument");
     if (gnum < 2) return fail(h, REO_ERR_DIM, "Only 1 level in 'group', at least 2 levels!");
@@ -547,7 +547,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         // non-integral values: the 0.1 tie band of is_greater (src:72) is not transitive, so ranks cannot be
         // used -- stage the raw values as FP64 and let the pair kernel compare them directly
         if (dtype != REO_F64 && dtype != REO_F32) return fail(h, REO_ERR_ARG, "non-integral values in an integer matrix");
-        S.flt = true; S.B = 0; S.NP = 1;
+        S.flt = true; S.flt_f32 = (dtype == REO_F32); S.B = 0; S.NP = 1;
     } else {
         const int distinct = std::max(D.h_counts[2], 1);
         int B = 1;
@@ -678,7 +678,7 @@ int launch_tables_v1(reo_handle_t h, ReoDev& D, const LevelPlan& P, const int32_
     p.njchunks = (ntc + p.jchunk - 1) / p.jchunk;
     p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
     p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;
-    p.flt = S.flt ? 1 : 0;
+    p.flt = S.flt ? (S.flt_f32 ? 2 : 1) : 0;
     CK(cudaMemsetAsync(D.counter.p, 0, sizeof(unsigned int), D.st));
     int rc = record_pair_events(h, D, true);
     if (rc) return rc;

@@ -46,6 +46,7 @@ struct ReoStaged {
     int NP = 0;        // planes = B + 1
     uint32_t* planes = nullptr;      // [NT][W][NP][64]; float path: [NT][W][REO_FLT_OPWORDS]
     bool flt = false;                // non-integral input: raw FP64 values instead of rank planes
+    bool flt_f32 = false;            // ... that came from a Float32 matrix: differences are rounded to Float32 (src:72 in Julia)
     std::vector<int> lev_word0;      // first word of each level
     std::vector<int> lev_words;      // words of each level
     std::vector<int> lev_n;          // real samples of each level
@@ -78,7 +79,8 @@ struct ReoPairParams {
     uint32_t maskA, maskB;
     int KW;                      // sample words per pipeline slot (set by the launcher)
     int use_lut, lutSZA, lutSZB; // class lookup tables in shared memory (set by the launcher)
-    int flt;                     // 1: planes hold raw FP64 values (REO_FLT_OPWORDS words per operand word)
+    int flt;                     // 1: planes hold raw FP64 values (REO_FLT_OPWORDS words per operand word); 2: the same,
+                                 //    from a Float32 matrix (x - y is rounded to Float32 before the 0.1 test)
     unsigned int one;            // == 1 (see mad_acc in reo_pairs.cu)
 };
 

@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : (NB == 8 ? 2 : PK_CTAS_P
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) { gtm[a][b] = 0u; lem[a][b] = 0u; }
+                const bool f32 = p.flt == 2;
                 const double* xd = reinterpret_cast<const double*>(srow + kk * op_words + REO_TILE) + ty * 4;
                 const double* yd = reinterpret_cast<const double*>(scol + kk * op_words + REO_TILE) + tx * 4;
 #pragma unroll 2
@@ -344,7 +345,8 @@ __global__ void __launch_bounds__(PK_THREADS, FLT ? 2 : (NB == 8 ? 2 : PK_CTAS_P
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
-                            const double d = x[a] - y[b];
+                            // Matrix{Float32}: Julia rounds x - y to Float32 before comparing with the Float64 literal 0.1
+                            const double d = f32 ? (double)(__double2float_rn(x[a]) - __double2float_rn(y[b])) : x[a] - y[b];
                             if (d >= 0.1) gtm[a][b] |= bit;
                             if (d > -0.1) lem[a][b] |= bit;
                         }
@@ -556,7 +558,7 @@ __global__ void pair_counts_small_kernel(const uint32_t* __restrict__ planes, in
                                          const int32_t* __restrict__ word_order, int WA,
                                          const int32_t* __restrict__ rows, int nrows,
                                          const int32_t* __restrict__ cols, int ncols, int32_t* nre, int32_t* rest,
-                                         int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB) {
+                                         int padA, int padB, int mixed, uint32_t maskA, uint32_t maskB, int f32) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * ncols) return;
     const int gi = rows[idx / ncols], gj = cols[idx % ncols];
@@ -573,7 +575,8 @@ __global__ void pair_counts_small_kernel(const uint32_t* __restrict__ planes, in
             const uint32_t coin = bi[gi & 63] ^ bj[gj & 63] ^ om;
             uint32_t bor = 0u;
             for (int sidx = 0; sidx < 32; ++sidx) {
-                const double d = xi[sidx * REO_TILE] - yj[sidx * REO_TILE];
+                const double xv = xi[sidx * REO_TILE], yv = yj[sidx * REO_TILE];
+                const double d = f32 ? (double)(__double2float_rn(xv) - __double2float_rn(yv)) : xv - yv;
                 const uint32_t gt = d >= 0.1, tie = (d > -0.1) && !(d >= 0.1);
                 bor |= (gt | (tie & (coin >> sidx))) << sidx;
             }
@@ -612,6 +615,6 @@ cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word
     const int n = nrows * ncols;
     if (n <= 0) return cudaSuccess;
     pair_counts_small_kernel<<<(n + 127) / 128, 128, 0, st>>>(S.planes, S.W, S.flt ? 0 : S.NP, word_order, WA, rows, nrows, cols,
-                                                              ncols, nre, rest, padA, padB, mixed, maskA, maskB);
+                                                              ncols, nre, rest, padA, padB, mixed, maskA, maskB, S.flt_f32 ? 1 : 0);
     return cudaGetLastError();
 }

@@ -397,6 +397,31 @@ def test_more_than_65535_samples_per_group_wide_counters(reo, oracle, coracle):
     assert np.array_equal(reo.tables(0, np.ones(r, bool), thresholds=thr), tab_all)
 
 
+def test_float32_differences_are_rounded_to_float32(reo, oracle, coracle):
+    """Matrix{Float32}: Julia evaluates abs(x - y) in Float32 and compares the result with the Float64 literal 0.1
+    (src:72), so 0.07f0 - (-0.03f0) = 0.1f0 is NOT a tie although the exact difference is below 0.1.  Values on a 0.01
+    grid put thousands of pairs on the edge of the band."""
+    rng = np.random.default_rng(12)
+    r, n1, n2 = 90, 21, 19
+    data = (rng.integers(-20, 21, size=(r, n1 + n2)) / 100.0).astype(np.float32)
+    data[:12, n1:] += np.float32(0.2)
+    gid = np.array([0] * n1 + [1] * n2, dtype=np.int32)
+    rows = np.arange(r)
+    want32 = oracle.greater_counts(data, gid, 2, rows, rows, seed=7)
+    want64 = oracle.greater_counts(data.astype(np.float64), gid, 2, rows, rows, seed=7)
+    assert not np.array_equal(want32, want64)          # the two semantics really differ on this matrix
+    reo.stage(data, gid, 2)
+    nre, rest = reo.pair_counts(0, rows, rows)
+    assert np.array_equal(nre, want32[0]) and np.array_equal(rest, want32[1])
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    mask = np.arange(r) % 4 != 0
+    tab, _ = coracle.block_tables(data, gid, 2, thr, np.nonzero(mask)[0], seed=7)          # C oracle: float32 semantics too
+    assert np.array_equal(reo.tables(0, mask, thresholds=thr), tab)
+    reo.stage(data.astype(np.float64), gid, 2)           # the same values as Matrix{Float64}: exact differences
+    nre64, rest64 = reo.pair_counts(0, rows, rows)
+    assert np.array_equal(nre64, want64[0]) and np.array_equal(rest64, want64[1])
+
+
 def test_subset_and_detect_more_than_65535_cells(reo):
     """gridDim.y is capped at 65535: the kernels next to the path stride over the cell dimension."""
     rng = np.random.default_rng(3)
