@@ -1,4 +1,7 @@
-// reo_pairs.cu -- K2: the pair-count / stable-REO class / per-gene 9-bin table kernel.
+// reo_pairs.cu -- K2, FIRST GENERATION: the pair-count / stable-REO class / per-gene 9-bin table kernel of round 1.
+// Since round 2 the rank path runs reo_pairs2.cu (warp-specialised, symmetric sweep); this kernel is kept for the
+// raw-FP64 variant (FLT: non-integral expression values), for the small-block parity kernel at the end of
+// the file, and -- with run-time plane count only -- for A/B runs of the rank path (REO_PAIRS_V1=1).
 //
 // Reference semantics (src/RankCompV3.jl): for every gene i and every reference gene j != i
 //   nre  = #{ s in group k   : is_greater(x[i,s], x[j,s]) }                       (src:372-373)
@@ -544,13 +547,7 @@ cudaError_t reo_launch_pairs(const ReoPairParams& p, int num_sms, cudaStream_t s
         return q.use_lut ? launch_np_lut<0, true, true>(q, lut_words, num_sms, st)
                          : launch_np_lut<0, false, true>(q, lut_words, num_sms, st);
     }
-    switch (p.NP) {
-#define CASE_NP(n) case n: return launch_np<n>(p, num_sms, st);
-        CASE_NP(2) CASE_NP(3) CASE_NP(4) CASE_NP(5) CASE_NP(6) CASE_NP(7) CASE_NP(8) CASE_NP(9) CASE_NP(10)
-        CASE_NP(11) CASE_NP(12) CASE_NP(13) CASE_NP(14) CASE_NP(15) CASE_NP(16) CASE_NP(17)
-#undef CASE_NP
-        default: return launch_np<0>(p, num_sms, st);
-    }
+    return launch_np<0>(p, num_sms, st);   // run-time plane count (the specialised chains live in reo_pairs2.cu)
 }
 
 // ---- small-block debug/parity kernel: one thread per (row, col) pair, straight from the planes ----
