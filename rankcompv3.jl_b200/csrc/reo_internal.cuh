@@ -100,7 +100,7 @@ struct ReoPair2Params {
     unsigned int* counter;       // dynamic work counter (zeroed before launch)
     int ntr, ntc, nsym;          // row tiles, column tiles, symmetric row tiles
     int T;                       // block edge in tiles (even): one work item = T row tiles x T column tiles
-    int SS;                      // supertile edge in blocks (L2 locality)
+    int SS, SSc;                 // supertile edge in blocks (L2 locality): rows, columns (SSc < SS only without a symmetric region)
     int perm_mul;                // unit modulo SS*SS*RS that scrambles the item order inside a supertile
     int RS;                      // row parts per block: one work item = T / RS row tiles x T column tiles
     int NBs, NBr, NBc;           // blocks: symmetric rows, all rows, columns

@@ -22,6 +22,7 @@
 //    and supertiles are dealt round-robin to the ranks of a multi-GPU job (tables are summed across ranks).
 // Arithmetic is unchanged: bit-sliced borrow chain, ONE LOP3 (0xB2) per rank plane per 32 samples, tie coin as
 // plane 0, POPC + IMAD accumulation, lookup-table classification.  Bound: the ALU (LOP3) pipe; no tensor cores.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -68,7 +69,7 @@ __device__ __forceinline__ void p2_consumer_bar() { asm volatile("bar.sync 1, %0
 // every rank gets the same number of items of every supertile (+-1), whatever the shape of the tile space.
 __host__ __device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int n, int& bi, int& bj, int& sub) {
     const long long g = (long long)n * p.world + p.rank;
-    const int per_sup = p.SS * p.SS * p.RS;
+    const int per_sup = p.SS * p.SSc * p.RS;
     const long long s = g / per_sup;
     if (s >= p.NSUP) return false;
     // inside a supertile the items are visited in a scrambled order (multiplication by a unit modulo their number):
@@ -76,7 +77,7 @@ __host__ __device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int 
     const int li0 = (int)(((g - s * per_sup) * p.perm_mul + s) % per_sup);
     const int li = li0 / p.RS;
     sub = li0 - li * p.RS;
-    const int di = li / p.SS, dj = li - di * p.SS;
+    const int di = li / p.SSc, dj = li - di * p.SSc;
     if (s < p.tri) {   // symmetric region: supertile row SI holds supertile columns SI .. Ms-1
         int si = 0;
         long long off = 0;
@@ -87,7 +88,7 @@ __host__ __device__ __forceinline__ bool p2_decode(const ReoPair2Params& p, int 
     }
     const long long s2 = s - p.tri;
     bi = p.NBs + (int)(s2 / p.Mc) * p.SS + di;
-    bj = (int)(s2 % p.Mc) * p.SS + dj;
+    bj = (int)(s2 % p.Mc) * p.SSc + dj;
     return bi < p.NBr && bj < p.NBc;
 }
 
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
     uint32_t om = 0u;          // tie-coin orientation [i<j] of this thread's pairs (all-ones / zero) ...
     uint32_t obits = 0u;       // ... and per pair (bit a*NB+b), used only when the 4 x 8 block is not uniform
     bool uniform = true;       // one orientation, every gene real, no self pair
+    int wpath = 0;             // word loop of this warp: 0 one orientation, 1 per column, 2 per pair
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -331,10 +333,26 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
             }
     };
 
+#ifdef REO_P2_TRACE
+    // -DREO_P2_TRACE: every consumer warp prints where its time went (one line per warp of a CTA that did work):
+    // hardware warp slot, stages, items, time spent waiting for operands, time in the kernel, word-loop variant
+    unsigned long long tr_t0, tr_first = 0ull, tr_items = 0ull, tr_wait = 0ull; int tr_nst = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
+#endif
     int slot = 0;
     uint32_t phase = 0u;
     for (;;) {
+#ifdef REO_P2_TRACE
+        unsigned long long tr_w0, tr_w1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_w0));
+#endif
         mbar_wait_parked(&full[slot], phase);
+#ifdef REO_P2_TRACE
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_w1));
+        if (tr_first == 0ull) tr_first = tr_w1;
+        else tr_wait += tr_w1 - tr_w0;
+        ++tr_nst;
+#endif
         const P2Aux* A = &aux[slot];
         const int4 hdr = *reinterpret_cast<const int4*>(&A->flags);
         const int flags = hdr.x;
@@ -360,6 +378,12 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
 #pragma unroll
                     for (int b = 0; b < NB; ++b) obits |= (uint32_t)(gi[a] < gj[b]) << (a * NB + b);
                 om = (obits & 1u) ? 0xffffffffu : 0u;
+            }
+            // the word loop is chosen per warp (no divergence): one orientation for every lane's block; per column;
+            // per pair
+            {
+                const bool colok = obits == (obits & 0xffu) * 0x01010101u;
+                wpath = __all_sync(0xffffffffu, uniform) ? 0 : (__all_sync(0xffffffffu, colok) ? 1 : 2);
             }
             if (LUT) {
                 const uint32_t a0 = lut_s + (om & (uint32_t)(SZA * 4));
@@ -391,6 +415,9 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
         // UNI: one tie-coin orientation for the whole 4 x 8 block (all but the blocks on the diagonal / matrix edges)
         auto words = [&](auto uni_c) {
             constexpr bool UNI = decltype(uni_c)::value;
+            // column flags of the orientation in the top bit of each byte (columns 0..3 / 4..7), for PRMT
+            const uint32_t cfA = ((obits & 1u) << 7) | ((obits & 2u) << 14) | ((obits & 4u) << 21) | ((obits & 8u) << 28);
+            const uint32_t cfB = ((obits & 16u) << 3) | ((obits & 32u) << 10) | ((obits & 64u) << 17) | ((obits & 128u) << 24);
             uint4 xn = lds_v4(xa), yn = lds_v4(ya), zn = lds_v4(ya + zoff);
             // borrow chain of one word over all planes; leaves the operands of the next word's plane 0 in xn/yn/zn
             auto chain = [&](uint32_t (&bor)[4][NB]) {
@@ -398,16 +425,30 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                     const uint32_t x[4] = {xn.x, xn.y, xn.z, xn.w};
                     const uint32_t y[NB] = {yn.x, yn.y, yn.z, yn.w, zn.x, zn.y, zn.z, zn.w};
                     xn = lds_v4(xa + 256u); yn = lds_v4(ya + 256u); zn = lds_v4(ya + zoff + 256u);   // plane 1
+                    if (UNI) {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b)
+                        for (int b = 0; b < NB; ++b)
 #pragma unroll
-                        for (int a = 0; a < 4; ++a) bor[a][b] = lop3_xor3(x[a], y[b], om);
-                }
-                if (!UNI) {   // rare: flip the coin seed of the pairs whose orientation differs from pair (0,0)
+                            for (int a = 0; a < 4; ++a) bor[a][b] = lop3_xor3(x[a], y[b], om);
+                    } else if (wpath == 1) {
+                        // the orientation depends on the column only (a block the column list's order crosses):
+                        // one PRMT per column replicates its flag into a full word
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                        for (int b = 0; b < NB; ++b) {
+                            const uint32_t d = prmt_sign(b < 4 ? cfA : cfB, 0x8888u + 0x1111u * (uint32_t)(b & 3));
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) bor[a][b] ^= (0u - (((obits >> (a * NB + b)) ^ obits) & 1u));
+                            for (int a = 0; a < 4; ++a) bor[a][b] = lop3_xor3(x[a], y[b], d);
+                        }
+                    } else {
+                        // any orientation per pair (diagonal blocks, blocks that hold a pad or the row gene itself)
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) {
+                                const uint32_t d = (uint32_t)((int)(obits << (31 - (a * NB + b))) >> 31);
+                                bor[a][b] = lop3_xor3(x[a], y[b], d);
+                            }
+                    }
                 }
                 if (NPT > 0) {
 #pragma unroll
@@ -464,7 +505,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                 ++done;
             }
         };
-        if (uniform) words(std::true_type{}); else words(std::false_type{});
+        if (wpath == 0) words(std::true_type{}); else words(std::false_type{});
         if (flags & P2F_LAST_J) {
             // group B finished: look up the bin; the pair adds sign(j) to bin q of its row gene and, in the symmetric
             // region, sign(i) to the mirrored bin (8 - q, 0-based; src:385-386) of its column gene.  Signs, gene ids
@@ -537,8 +578,23 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
             }
             p2_consumer_bar();
         }
+#ifdef REO_P2_TRACE
+        if (last_item) ++tr_items;
+#endif
         if (++slot == NS) { slot = 0; phase ^= 1u; }
     }
+#ifdef REO_P2_TRACE
+    if (lane == 0 && tr_nst > 1) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        unsigned smid, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        printf("[p2 trace] cta %d warp %d sm %u slot %u first %.1f stages %d items %llu wait %.1f total %.1f path %d\n", blockIdx.x,
+               warp, smid, wid, (double)(tr_first - tr_t0) * 1e-3, tr_nst, tr_items, (double)tr_wait * 1e-3,
+               (double)(t1 - tr_t0) * 1e-3, wpath);
+    }
+#endif
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -584,8 +640,11 @@ static void p2_geometry(ReoPair2Params& p) {
     if (forced_ss > 0) SS = forced_ss;
     for (;;) {
         p.SS = SS;
+        // no symmetric region: a supertile is not wider than the column blocks there are (few columns: no item index
+        // without work, so a short launch gets exactly one CTA per item)
+        p.SSc = p.nsym > 0 ? SS : std::min(SS, p.NBc);
         p.Ms = (p.NBs + SS - 1) / SS;
-        p.Mc = (p.NBc + SS - 1) / SS;
+        p.Mc = (p.NBc + p.SSc - 1) / p.SSc;
         const int Mr = (p.NBr - p.NBs + SS - 1) / SS;
         p.tri = (long long)p.Ms * (p.Ms + 1) / 2;
         p.NSUP = p.tri + (long long)Mr * p.Mc;
@@ -597,13 +656,13 @@ static void p2_geometry(ReoPair2Params& p) {
     p.RS = ((long long)p.W * p.NP >= 1024) ? T : 1;
     if (forced_rs > 0 && T % forced_rs == 0) p.RS = forced_rs;
     {
-        const int per_sup = p.SS * p.SS * p.RS;
+        const int per_sup = p.SS * p.SSc * p.RS;
         int m = 7;
         while (std::__gcd(m, per_sup) != 1) m += 2;
         p.perm_mul = per_sup > 1 ? m % per_sup : 1;
         if (p.perm_mul == 0) p.perm_mul = 1;
     }
-    const long long total_items = p.NSUP * p.SS * p.SS * p.RS;
+    const long long total_items = p.NSUP * p.SS * p.SSc * p.RS;
     const long long mine = total_items > p.rank ? (total_items - p.rank + p.world - 1) / p.world : 0;
     p.nitems = (int)std::min<long long>(mine, 0x7fffffff);
 }

@@ -80,6 +80,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// byte permute; a selector nibble 8 + k replicates the top bit of byte k of `a` over the result byte
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %1, %2;" : "=r"(d) : "r"(a), "r"(sel));
+    return d;
+}
 // borrow' = (x & ~y) | (~(x ^ y) & c)
 __device__ __forceinline__ uint32_t lop3_b2(uint32_t x, uint32_t y, uint32_t c) {
     uint32_t d;
