@@ -458,6 +458,9 @@ def main():
                        "sharding": f"supertiles of the pair-tile space round-robin over {world} rank(s), tables summed via {args.collective}"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "input": "pinned host memory",
                     "h2d_bytes_per_step": int(nbytes + gid.nbytes + ref.nbytes),
+                    "h2d_note": "bytes of the caller's host matrix per step; the library's copy threads narrow integral "
+                                "values in 0..65535 to u16 on their way through the pinned bounce buffers, so PCIe carries "
+                                "a quarter of an Int64 matrix (csrc/reo_host.cpp; REO_NO_NARROW=1 sends it raw)",
                     "d2h_bytes_per_step": int(r * 15 * 8 + 2 * r), "pageable": e2e_pageable},
             "gpu_launches": int(launches),
             "stage_ms": {"staging": st_dev[-1]["ms_stage"], "pairs": st_dev[-1]["ms_pairs"],

@@ -189,9 +189,26 @@ struct reo_handle_s {
     std::vector<reo_handle_s*> subs;
     std::vector<LevelLog> logs;   // per level k of the last reo_identify_degs
     int64_t ordered_triples = 0;  // rows x columns x samples the evaluated pairs stand for (W_ord of SURVEY 8d)
+    bool no_narrow = false;       // do_stage retry: copy a pageable matrix raw (it turned out to hold non-integral values)
 };
 
+// reo_host.cpp: narrowing copies of the pageable-input pipeline (1 = every value was an integer in 0..65535)
+extern "C" int reo_host_narrow_i64(const int64_t* src, uint16_t* dst, size_t n);
+extern "C" int reo_host_narrow_i32(const int32_t* src, uint16_t* dst, size_t n);
+extern "C" int reo_host_narrow_f64(const double* src, uint16_t* dst, size_t n);
+extern "C" int reo_host_narrow_f32(const float* src, uint16_t* dst, size_t n);
+
 namespace {
+
+int host_narrow(int dtype, const void* src, uint16_t* dst, size_t n) {
+    switch (dtype) {
+        case REO_I64: return reo_host_narrow_i64((const int64_t*)src, dst, n);
+        case REO_I32: return reo_host_narrow_i32((const int32_t*)src, dst, n);
+        case REO_F64: return reo_host_narrow_f64((const double*)src, dst, n);
+        case REO_F32: return reo_host_narrow_f32((const float*)src, dst, n);
+        default: return 0;
+    }
+}
 
 int fail(reo_handle_t h, int code, const std::string& msg) {
     if (h) h->err = msg;
@@ -409,8 +426,8 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
 
     CK(D.ranks.ensure((size_t)nslots * rpad * (rank_bytes / 2)));
     // no clearing: bitplanes_kernel masks pad slots and genes >= r itself
-    CK(D.flags.ensure(8));
-    CK(cudaMemsetAsync(D.flags.p, 0, 8 * sizeof(int), D.st));
+    CK(D.flags.ensure(16));
+    CK(cudaMemsetAsync(D.flags.p, 0, 16 * sizeof(int), D.st));
     CK(D.fblist.ensure(std::max<int64_t>(nmy, 1)));
     CK(D.widelist.ensure(std::max<int64_t>(nmy, 1)));
 
@@ -438,7 +455,29 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         static const bool no_bounce = getenv("REO_NO_BOUNCE") != nullptr;
         if (no_bounce) pageable = false;
     }
-    if (pageable) {
+    // Host count matrices are narrowed to u16 while they pass through the bounce buffers (reo_host.cpp) -- pageable
+    // ones, which need the bounce anyway, and page-locked ones too as long as their chunks do narrow (the copy threads
+    // read host memory faster than PCIe carries 8-byte elements); a page-locked chunk that does not is sent by DMA
+    // straight from the caller's memory, and so are all later ones.
+    // the caller blocks in this call: all host cores copy (B200 host, 16 cores: 8 threads narrow 73 GB/s of input, 16
+    // threads 86), shared evenly between the ranks of one box
+    int copy_threads = 16;
+    if (const char* e = getenv("REO_COPY_THREADS")) copy_threads = atoi(e);
+    {
+        const int hc = (int)std::thread::hardware_concurrency();
+        if (hc > 0) copy_threads = std::min(copy_threads, std::max(1, hc / std::max(1, h->world)));
+        copy_threads = std::max(1, copy_threads);
+    }
+    static const bool no_narrow_env = getenv("REO_NO_NARROW") != nullptr;
+    bool try_narrow = !on_dev && !no_narrow_env && !h->no_narrow;
+    {
+        static const bool no_bounce = getenv("REO_NO_BOUNCE") != nullptr;
+        if (no_bounce) try_narrow = false;
+        // page-locked input: DMA needs no CPU at all, narrowing only wins with enough threads to outrun PCIe (measured:
+        // 16 threads 270 ms against 287 ms by plain DMA for the 4.8 GB matrix, 8 threads 325 ms)
+        if (!pageable && copy_threads < 12) try_narrow = false;
+    }
+    if (pageable || try_narrow) {
         const size_t need = (size_t)chunk * r * es;
         if (need > D.bounce_cap) {
             for (auto& bptr : D.bounce) { if (bptr) cudaFreeHost(bptr); bptr = nullptr; }
@@ -447,40 +486,57 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
             D.bounce_cap = need;
         }
         for (auto& e : D.bounce_ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        if (!D.pool) {
-            int nt = 8;
-            if (const char* e = getenv("REO_COPY_THREADS")) nt = atoi(e);
-            const int hc = (int)std::thread::hardware_concurrency();
-            if (hc > 0) nt = std::min(nt, std::max(1, hc / std::max(1, h->world)));
-            D.pool = new CopyPool(std::max(1, nt));
-        }
+        if (!D.pool) D.pool = new CopyPool(copy_threads);
     }
+    bool narrowed_any = false;
     if (!on_dev) {   // the copy stream must not overtake work still queued on `st` that reads/frees `raw`
         CK(cudaEventRecord(D.ev[5], D.st));
         CK(cudaStreamWaitEvent(D.st_copy, D.ev[5], 0));
     }
-    size_t n_chunk = 0;
+    size_t n_chunk = 0, n_narrow = 0;
+    bool bounce_used[REO_NBOUNCE] = {};
     const bool small_first = c >= 1024;   // heuristic only: either order of tiers gives the same ranks
     for (int64_t j0 = 0; j0 < nmy;) {
         int64_t n = 1;   // run of consecutive original columns, at most `chunk` long
         while (j0 + n < nmy && n < chunk && my_samples[j0 + n] == my_samples[j0] + n) ++n;
+        bool chunk_narrow = false;
         if (!on_dev) {
             // copy on the copy stream, rank on the compute stream as soon as this chunk has landed
             const uint8_t* src = (const uint8_t*)data + (size_t)my_samples[j0] * ld * es;
-            if (pageable) {
-                // pageable input (a Julia Matrix): a few host threads fill a pinned bounce buffer while the DMA engine
-                // drains the previous ones -- the driver's own pageable path is several times slower than PCIe
+            if (pageable || try_narrow) {
+                // a few host threads fill a pinned bounce buffer while the DMA engine drains the previous ones (for a
+                // pageable matrix the driver's own path is several times slower than PCIe)
                 const int b = (int)(n_chunk % REO_NBOUNCE);
-                if (n_chunk >= REO_NBOUNCE) CK(cudaEventSynchronize(D.bounce_ev[b]));
+                if (bounce_used[b]) CK(cudaEventSynchronize(D.bounce_ev[b]));   // its previous chunk has left the buffer
                 uint8_t* dstb = D.bounce[b];
                 const size_t colb = (size_t)r * es, ldb = (size_t)ld * es;
-                D.pool->run([&](int part, int nparts) {
-                    const int64_t c0 = n * part / nparts, c1 = n * (part + 1) / nparts;
-                    if (ldb == colb) { if (c1 > c0) memcpy(dstb + c0 * colb, src + c0 * colb, (size_t)(c1 - c0) * colb); }
-                    else for (int64_t q = c0; q < c1; ++q) memcpy(dstb + q * colb, src + q * ldb, colb);
-                });
-                CK(cudaMemcpyAsync(D.raw.p + (size_t)j0 * r * es, dstb, (size_t)n * colb, cudaMemcpyHostToDevice, D.st_copy));
-                CK(cudaEventRecord(D.bounce_ev[b], D.st_copy));
+                if (try_narrow) {
+                    std::atomic<int> all_small{1};
+                    D.pool->run([&](int part, int nparts) {
+                        const int64_t c0 = n * part / nparts, c1 = n * (part + 1) / nparts;
+                        for (int64_t q = c0; q < c1 && all_small.load(std::memory_order_relaxed); ++q)
+                            if (!host_narrow(dtype, src + q * ldb, (uint16_t*)dstb + q * r, (size_t)r)) all_small.store(0);
+                    });
+                    chunk_narrow = all_small.load() != 0;
+                    if (!chunk_narrow && !pageable) try_narrow = false;   // page-locked: plain DMA from here on
+                }
+                if (!chunk_narrow && pageable)
+                    D.pool->run([&](int part, int nparts) {
+                        const int64_t c0 = n * part / nparts, c1 = n * (part + 1) / nparts;
+                        if (ldb == colb) { if (c1 > c0) memcpy(dstb + c0 * colb, src + c0 * colb, (size_t)(c1 - c0) * colb); }
+                        else for (int64_t q = c0; q < c1; ++q) memcpy(dstb + q * colb, src + q * ldb, colb);
+                    });
+                narrowed_any |= chunk_narrow;
+                n_narrow += chunk_narrow ? 1 : 0;
+                if (chunk_narrow || pageable) {
+                    // a narrowed chunk lands at the start of the chunk's own place in `raw`
+                    CK(cudaMemcpyAsync(D.raw.p + (size_t)j0 * r * es, dstb, (size_t)n * (chunk_narrow ? (size_t)r * 2 : colb),
+                                       cudaMemcpyHostToDevice, D.st_copy));
+                    CK(cudaEventRecord(D.bounce_ev[b], D.st_copy));
+                    bounce_used[b] = true;
+                } else {
+                    CK(cudaMemcpy2DAsync(D.raw.p + (size_t)j0 * r * es, colb, src, ldb, colb, (size_t)n, cudaMemcpyHostToDevice, D.st_copy));
+                }
             } else {
                 CK(cudaMemcpy2DAsync(D.raw.p + (size_t)j0 * r * es, (size_t)r * es, src, (size_t)ld * es, (size_t)r * es,
                                      (size_t)n, cudaMemcpyHostToDevice, D.st_copy));
@@ -496,16 +552,26 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         }
         // tier 0: small presence bitmap (value range < 65536), 8 CTAs per SM; wider columns are listed for tier 1.
         // Bulk inputs (few samples, counts up to ~1e6) would all overflow it, so they start at tier 1 directly.
+        // (a narrowed chunk: u16 elements; the base is shifted so that column j of the list is at base + j * r elements)
+        const uint8_t* cdata = chunk_narrow ? D.raw.p + (size_t)j0 * r * (es - 2) : dev_data;
+        const int cdtype = chunk_narrow ? REO_U16_STAGED : dtype;
         if (small_first)
-            CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, j0, (int)n, nullptr, 0, d_src_col, d_sample_id,
+            CKL(reo_launch_rank_columns(cdata, cdtype, r, dev_ld, j0, (int)n, nullptr, 0, d_src_col, d_sample_id,
                                         D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p,
                                         D.flags.p + 3, D.widelist.p, D.st));
         else
-            CKL(reo_launch_rank_columns(dev_data, dtype, r, dev_ld, j0, (int)n, nullptr, 1, d_src_col, d_sample_id,
+            CKL(reo_launch_rank_columns(cdata, cdtype, r, dev_ld, j0, (int)n, nullptr, 1, d_src_col, d_sample_id,
                                         D.slot_of_sample.p, D.ranks.p, rank_bytes, rpad, D.flags.p + 2, D.flags.p,
                                         D.flags.p + 1, D.fblist.p, D.st));
         h->kernel_launches++;
         j0 += n;
+    }
+    if (!on_dev && getenv("REO_TIMING"))
+        fprintf(stderr, "[reo timing] rank %d %s host input: %zu copy chunks, %zu narrowed to u16\n", h->rank,
+                pageable ? "pageable" : "page-locked", n_chunk, n_narrow);
+    if (narrowed_any) {   // flags[4]: this rank narrowed a chunk (the retry below must be taken by every rank or none)
+        D.h_counts[8] = 1;
+        CK(cudaMemcpyAsync(D.flags.p + 4, D.h_counts + 8, sizeof(int), cudaMemcpyHostToDevice, D.st));
     }
     CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
     CK(cudaStreamSynchronize(D.st));
@@ -535,13 +601,22 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     }
     const bool more_ranked = (D.h_counts[3] > 0 || nfb > 0) && !D.h_counts[0];   // a later tier ran after the read-back
     if (shard) {   // non-integrality and the largest dense rank are properties of the whole matrix
-        const ncclResult_t nr = g_nccl.AllReduce(D.flags.p, D.flags.p + 4, 4, ncclInt32, ncclMax, D.comm, D.st);
+        const ncclResult_t nr = g_nccl.AllReduce(D.flags.p, D.flags.p + 8, 5, ncclInt32, ncclMax, D.comm, D.st);
         if (nr != ncclSuccess) return fail(h, REO_ERR_COMM, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(nr));
-        CK(cudaMemcpyAsync(D.h_counts, D.flags.p + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaMemcpyAsync(D.h_counts, D.flags.p + 8, 5 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
+        narrowed_any = D.h_counts[4] != 0;
     } else if (more_ranked) {
         CK(cudaMemcpyAsync(D.h_counts, D.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
+    }
+    if (D.h_counts[0] && narrowed_any) {
+        // some chunks hold non-integral values while others were narrowed to u16: the float path needs the raw matrix
+        // on the device, so stage once more without narrowing (every rank takes this branch or none does)
+        h->no_narrow = true;
+        const int rc2 = do_stage(h, data, dtype, r, c, ld, group_id, gnum, flags);
+        h->no_narrow = false;
+        return rc2;
     }
     if (D.h_counts[0]) {
         // non-integral values: the 0.1 tie band of is_greater (src:72) is not transitive, so ranks cannot be

@@ -136,6 +136,7 @@ cudaError_t reo_launch_pair_counts_small(const ReoStaged& S, const int32_t* word
 // list position j -> data column src_col[j], original sample sample_id[j].
 // Two bitmap tiers: wide == 0 -> 256 threads, range < 65536, 8 CTAs/SM; wide != 0 -> 1024 threads, range < 1.3 M,
 // 1 CTA/SM.  cols (optional) lists the positions to process; columns that do not fit go to over_list/over_count.
+#define REO_U16_STAGED 100   // internal element type: a chunk of the input narrowed to u16 by the host (reo_host.cpp)
 cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int64_t ld, int64_t col0, int ncols,
                                     const int32_t* cols, int wide, const int32_t* src_col, const int32_t* sample_id,
                                     const int32_t* slot_of_sample, void* ranks, int rank_bytes, int64_t rpad,

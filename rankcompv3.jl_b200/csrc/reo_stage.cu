@@ -30,6 +30,8 @@ __device__ __forceinline__ bool to_ll<long long>(long long v, long long& out) { 
 template <>
 __device__ __forceinline__ bool to_ll<int>(int v, long long& out) { out = v; return true; }
 template <>
+__device__ __forceinline__ bool to_ll<unsigned short>(unsigned short v, long long& out) { out = v; return true; }
+template <>
 __device__ __forceinline__ bool to_ll<double>(double v, long long& out) {
     if (!(fabs(v) < 4.0e18) || v != rint(v)) return false;
     out = (long long)v;
@@ -396,6 +398,7 @@ cudaError_t reo_launch_rank_columns(const void* data, int dtype, int64_t r, int6
         case REO_F64: LAUNCH_RK(double)
         case REO_I32: LAUNCH_RK(int)
         case REO_F32: LAUNCH_RK(float)
+        case REO_U16_STAGED: LAUNCH_RK(unsigned short)
         default: return cudaErrorInvalidValue;
     }
 #undef LAUNCH_RK

@@ -380,6 +380,43 @@ def test_iter_log_per_level_and_input_memory_kinds(reo, pkg, oracle, coracle):
         assert np.array_equal(o.result, out.result) and np.array_equal(o.updown, out.updown)
 
 
+def test_pageable_input_is_narrowed_chunk_by_chunk(reo, oracle, coracle):
+    """Pageable host matrices are narrowed to u16 by the copy threads, chunk by chunk (csrc/reo_host.cpp): a chunk with a
+    value above 65535 travels raw, and a matrix with a non-integral value in one chunk only is staged again without
+    narrowing (float path).  Every variant must give the tables of the same matrix in page-locked memory, and the
+    oracle's."""
+    import torch
+    rng = np.random.default_rng(77)
+    r, n1, n2 = 1200, 1500, 1500                     # 2 copy chunks of <= 1628 columns
+    mu = np.exp(rng.normal(0.5, 1.2, r))
+    base = rng.poisson(mu[:, None] * np.ones((1, n1 + n2))).astype(np.int64)
+    base[:40, n1:] += 3
+    gid = np.array([0] * n1 + [1] * n2, dtype=np.int32)
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    mask = np.zeros(r, bool)
+    mask[rng.choice(r, 24, replace=False)] = True
+
+    def tables_of(mat):
+        reo.stage(mat, gid, 2)
+        return reo.tables(0, mask, thresholds=thr)
+
+    def pinned_copy(mat):
+        t = torch.from_numpy(np.ascontiguousarray(mat.T)).pin_memory()
+        return t, t.numpy().T
+
+    cases = []
+    wide = base.copy(); wide[17, 2500] = 70000      # second chunk cannot be narrowed
+    cases += [base, wide, base.astype(np.int32), base.astype(np.float64), base.astype(np.float32)]
+    frac = base.astype(np.float64); frac[33, 2900] += 0.25      # non-integral value in the second chunk only
+    cases.append(frac)
+    for mat in cases:
+        got = tables_of(np.asfortranarray(mat))                 # pageable
+        keep, pm = pinned_copy(mat)
+        assert np.array_equal(got, tables_of(pm))
+        want, _ = coracle.block_tables(mat, gid, 2, thr, np.nonzero(mask)[0], seed=7)
+        assert np.array_equal(got, want)
+
+
 def test_more_than_65535_samples_per_group_wide_counters(reo, oracle, coracle):
     """> 65 535 sample slots in a group: the pair kernel's packed 16-bit counters do not fit and the 32-bit variant runs."""
     rng = np.random.default_rng(9)
