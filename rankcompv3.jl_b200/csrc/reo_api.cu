@@ -495,6 +495,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     }
     size_t n_chunk = 0, n_narrow = 0;
     bool bounce_used[REO_NBOUNCE] = {};
+    static const int raw_every = getenv("REO_RAW_EVERY") ? atoi(getenv("REO_RAW_EVERY")) : 3;
     const bool small_first = c >= 1024;   // heuristic only: either order of tiers gives the same ranks
     for (int64_t j0 = 0; j0 < nmy;) {
         int64_t n = 1;   // run of consecutive original columns, at most `chunk` long
@@ -510,7 +511,11 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
                 if (bounce_used[b]) CK(cudaEventSynchronize(D.bounce_ev[b]));   // its previous chunk has left the buffer
                 uint8_t* dstb = D.bounce[b];
                 const size_t colb = (size_t)r * es, ldb = (size_t)ld * es;
-                if (try_narrow) {
+                // page-locked input: every raw_every-th chunk goes by plain DMA while the copy threads narrow the
+                // others -- PCIe and the host cores then work side by side (the DMA of a raw chunk takes about as long
+                // as narrowing two)
+                const bool dma_turn = !pageable && raw_every > 0 && (n_chunk % (size_t)raw_every) == (size_t)raw_every - 1;
+                if (try_narrow && !dma_turn) {
                     std::atomic<int> all_small{1};
                     D.pool->run([&](int part, int nparts) {
                         const int64_t c0 = n * part / nparts, c1 = n * (part + 1) / nparts;
