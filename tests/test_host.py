@@ -137,3 +137,34 @@ def test_pinned_output_pool_recycles_and_caps(pkg, monkeypatch):
     assert st.freed == [p0] and api._pinned_pooled == 0
 
 
+
+
+def test_host_narrowing_copies(pkg):
+    """csrc/reo_host.cpp (host code, no GPU): the copy threads narrow a chunk of the caller's matrix to u16 only if every
+    value is an integer in 0..65535; anything else must be reported so that the chunk travels raw."""
+    lib = pkg._lib.load()
+    rng = np.random.default_rng(5)
+    n = 4099                                                    # not a multiple of any vector width
+    good = rng.integers(0, 65536, n)
+    good[:3] = (0, 65535, 1)
+    cases = {
+        "reo_host_narrow_i64": (np.int64, [65536, -1, 1 << 40, -(1 << 62)]),
+        "reo_host_narrow_i32": (np.int32, [65536, -1, -(1 << 31)]),
+        "reo_host_narrow_f64": (np.float64, [65536.0, -1.0, 0.5, 1e-300, 1e20, 2.0 ** 52, np.nan, np.inf, -np.inf, 3.0000000000000004]),
+        "reo_host_narrow_f32": (np.float32, [65536.0, -1.0, 0.5, 1e-30, 1e20, 2.0 ** 23, np.nan, np.inf, 2.5]),
+    }
+    for name, (dt, bads) in cases.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        src = good.astype(dt)
+        if dt in (np.float64, np.float32):
+            src[7] = -0.0                                        # minus zero is the integer 0
+        out = np.zeros(n, dtype=np.uint16)
+        assert fn(src.ctypes.data, out.ctypes.data, n) == 1, name
+        assert np.array_equal(out, src.astype(np.int64).astype(np.uint16)), name
+        for pos in (0, n // 2, n - 1):
+            for bad in bads:
+                b = src.copy()
+                b[pos] = bad
+                assert fn(b.ctypes.data, out.ctypes.data, n) == 0, (name, bad, pos)
