@@ -444,6 +444,7 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     if (!on_dev) {
         chunk = std::max<int64_t>(1, (int64_t)(16u << 20) / (int64_t)(r * es));
         chunk = std::max<int64_t>(D.num_sms, chunk / D.num_sms * D.num_sms);
+        if (const char* e = getenv("REO_CHUNK_COLS")) chunk = std::max<int64_t>(1, atoll(e));
     }
     chunk = std::max<int64_t>(chunk, 1);
     bool pageable = false;
@@ -518,6 +519,13 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
                 if (try_narrow && !dma_turn) {
                     std::atomic<int> all_small{1};
                     D.pool->run([&](int part, int nparts) {
+                        if (ldb == colb) {   // contiguous chunk: equal element ranges, whatever the number of columns
+                            const int64_t tot = n * r;
+                            const int64_t e0 = tot * part / nparts / 16 * 16;
+                            const int64_t e1 = part + 1 == nparts ? tot : tot * (part + 1) / nparts / 16 * 16;
+                            if (e1 > e0 && !host_narrow(dtype, src + e0 * es, (uint16_t*)dstb + e0, (size_t)(e1 - e0))) all_small.store(0);
+                            return;
+                        }
                         const int64_t c0 = n * part / nparts, c1 = n * (part + 1) / nparts;
                         for (int64_t q = c0; q < c1 && all_small.load(std::memory_order_relaxed); ++q)
                             if (!host_narrow(dtype, src + q * ldb, (uint16_t*)dstb + q * r, (size_t)r)) all_small.store(0);

@@ -5,10 +5,13 @@
 // to u16 on the fly: the host writes a quarter of the bytes, the DMA engine reads a quarter from host memory and PCIe
 // carries a quarter.  A slice with any value outside 0..65535 (or any non-integral value) reports failure and the chunk
 // is copied raw instead; the device ranks u16 slices exactly as it ranks the original type (dense ranks depend on the
-// values only).  Measured on the B200 host (16 cores, 8 copy threads): memcpy 52.8 GB/s of input, narrowing Int64 72.8.
+// values only).  Measured on the B200 host (16 cores, 16 copy threads): memcpy 75 GB/s of input, narrowing Int64 113.
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
 #define REO_CLONES __attribute__((target_clones("avx2", "default")))
@@ -18,7 +21,76 @@
 
 extern "C" {
 
-REO_CLONES int reo_host_narrow_i64(const int64_t* src, uint16_t* dst, size_t n) {
+#if defined(__x86_64__) && defined(__GNUC__)
+#define REO_HAVE_AVX2_PATH 1
+// 16 values per iteration: three saturating packs (the values that matter have zero upper bits) and one cross-lane
+// permute; 113 GB/s of input with 16 threads on the B200 host, against 85 for the compiler's own vectorisation and 128
+// for reading alone
+__attribute__((target("avx2"))) static int narrow_i64_avx2(const int64_t* src, uint16_t* dst, size_t n) {
+    __m256i acc = _mm256_setzero_si256();
+    const __m256i perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i));
+        const __m256i b = _mm256_loadu_si256((const __m256i*)(src + i + 4));
+        const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 8));
+        const __m256i d = _mm256_loadu_si256((const __m256i*)(src + i + 12));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(a, b), _mm256_or_si256(c, d)));
+        const __m256i ab = _mm256_packus_epi32(a, b);        // per 128-bit lane: a0 0 a1 0 b0 0 b1 0 (u16)
+        const __m256i cd = _mm256_packus_epi32(c, d);
+        const __m256i abcd = _mm256_packus_epi32(ab, cd);    // per lane: a0 a1 b0 b1 c0 c1 d0 d1
+        _mm256_storeu_si256((__m256i*)(dst + i), _mm256_permutevar8x32_epi32(abcd, perm));
+    }
+    uint64_t t[4];
+    _mm256_storeu_si256((__m256i*)t, acc);
+    uint64_t s = t[0] | t[1] | t[2] | t[3];
+    for (; i < n; ++i) { s |= (uint64_t)src[i]; dst[i] = (uint16_t)src[i]; }
+    return (s >> 16) == 0;
+}
+// the same on k = bits(v + 2^52) - bits(2^52), with the round trip (v + 2^52) - 2^52 == v checked per vector
+__attribute__((target("avx2"))) static int narrow_f64_avx2(const double* src, uint16_t* dst, size_t n) {
+    __m256i acc = _mm256_setzero_si256();
+    const __m256i perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    const __m256d magic = _mm256_set1_pd(4503599627370496.0);
+    const __m256i mbits = _mm256_set1_epi64x(0x4330000000000000ll);
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        __m256i k[4];
+        for (int q = 0; q < 4; ++q) {
+            const __m256d v = _mm256_loadu_pd(src + i + 4 * q);
+            const __m256d t = _mm256_add_pd(v, magic);
+            const __m256d bad = _mm256_cmp_pd(_mm256_sub_pd(t, magic), v, _CMP_NEQ_UQ);
+            k[q] = _mm256_sub_epi64(_mm256_castpd_si256(t), mbits);
+            acc = _mm256_or_si256(acc, _mm256_or_si256(k[q], _mm256_castpd_si256(bad)));
+        }
+        const __m256i ab = _mm256_packus_epi32(k[0], k[1]);
+        const __m256i cd = _mm256_packus_epi32(k[2], k[3]);
+        _mm256_storeu_si256((__m256i*)(dst + i), _mm256_permutevar8x32_epi32(_mm256_packus_epi32(ab, cd), perm));
+    }
+    uint64_t t4[4];
+    _mm256_storeu_si256((__m256i*)t4, acc);
+    uint64_t s = t4[0] | t4[1] | t4[2] | t4[3];
+    for (; i < n; ++i) {
+        const double v = src[i];
+        const double t = v + 4503599627370496.0;
+        uint64_t b;
+        memcpy(&b, &t, 8);
+        const uint64_t kk = b - 0x4330000000000000ull;
+        s |= kk | ((t - 4503599627370496.0) != v ? ~0ull : 0ull);
+        dst[i] = (uint16_t)kk;
+    }
+    return (s >> 16) == 0;
+}
+static bool have_avx2() {
+    static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+}
+#endif
+
+int reo_host_narrow_i64(const int64_t* src, uint16_t* dst, size_t n) {
+#ifdef REO_HAVE_AVX2_PATH
+    if (have_avx2()) return narrow_i64_avx2(src, dst, n);
+#endif
     uint64_t acc = 0;
     for (size_t i = 0; i < n; ++i) {
         const uint64_t v = (uint64_t)src[i];
@@ -40,7 +112,10 @@ REO_CLONES int reo_host_narrow_i32(const int32_t* src, uint16_t* dst, size_t n) 
 
 // v + 2^52 holds v in the low mantissa bits exactly when v is an integer in [0, 2^51); anything else (fraction, negative,
 // huge, NaN, infinity) fails the round trip or leaves high bits set
-REO_CLONES int reo_host_narrow_f64(const double* src, uint16_t* dst, size_t n) {
+int reo_host_narrow_f64(const double* src, uint16_t* dst, size_t n) {
+#ifdef REO_HAVE_AVX2_PATH
+    if (have_avx2()) return narrow_f64_avx2(src, dst, n);
+#endif
     uint64_t acc = 0;
     for (size_t i = 0; i < n; ++i) {
         const double v = src[i];
