@@ -19,7 +19,12 @@
 //  * work item = T x T tile block; row AND column tables of a block live in shared memory and are flushed with
 //    integer atomics once per item (two named barriers per item, none inside);
 //  * items are ordered by supertiles (SS x SS blocks) so that concurrently running CTAs share operand tiles in L2,
-//    and supertiles are dealt round-robin to the ranks of a multi-GPU job (tables are summed across ranks).
+//    and the items of every supertile are dealt round-robin to the ranks of a multi-GPU job (tables are summed
+//    across ranks);
+//  * the tie-coin orientation [i<j] of a thread's 4 x 8 pairs is one register in all but a few blocks; a WARP votes
+//    for one of three variants of the word loop (one orientation / per column via PRMT / per pair), so that the
+//    blocks the sorted column list crosses -- one column group of every tile pair of a small update -- cost 2 %
+//    instead of a second pass through the loop (profiles/r02_pair_kernel_trace.md).
 // Arithmetic is unchanged: bit-sliced borrow chain, ONE LOP3 (0xB2) per rank plane per 32 samples, tie coin as
 // plane 0, POPC + IMAD accumulation, lookup-table classification.  Bound: the ALU (LOP3) pipe; no tensor cores.
 #include <stdio.h>
