@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <dlfcn.h>
+#include <sched.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -465,7 +466,9 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     int copy_threads = 16;
     if (const char* e = getenv("REO_COPY_THREADS")) copy_threads = atoi(e);
     {
-        const int hc = (int)std::thread::hardware_concurrency();
+        int hc = (int)std::thread::hardware_concurrency();
+        cpu_set_t cs;   // a cpuset may leave this process fewer cores than the machine has
+        if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) hc = hc > 0 ? std::min(hc, CPU_COUNT(&cs)) : CPU_COUNT(&cs);
         if (hc > 0) copy_threads = std::min(copy_threads, std::max(1, hc / std::max(1, h->world)));
         copy_threads = std::max(1, copy_threads);
     }
