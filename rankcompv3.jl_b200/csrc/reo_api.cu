@@ -144,6 +144,7 @@ struct ReoDev {
     DBuf<uint8_t> raw, raw2, pb, sub;
     DBuf<uint16_t> ranks;
     DBuf<uint32_t> planes, panel, k1_send, k1_gather;
+    DBuf<uint8_t> word_np;
     DBuf<int32_t> slot_of_sample, sample_of_slot, word_order, iota, col_gene, changed_gene, table, perm, perm2, counts,
         fblist, widelist, small_i, stage_lists, table_red, table_all, list_gene;
     DBuf<int8_t> changed_sign, updown, list_sign;
@@ -670,6 +671,14 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
         CKL(reo_launch_unshard_planes(D.k1_gather.p, S.planes, S.NT, W, wq, (int)wb, D.st));
         h->kernel_launches += 2;
     }
+    S.word_np = nullptr;
+    static const bool no_skip = getenv("REO_NO_PLANE_SKIP") != nullptr;
+    if (!S.flt && !no_skip) {   // which planes each sample word really uses (the pair kernel skips an empty top plane)
+        CK(D.word_np.ensure((size_t)W));
+        CKL(reo_launch_word_planes(S.planes, S.NT, W, S.NP, D.word_np.p, D.st));
+        h->kernel_launches++;
+        S.word_np = D.word_np.p;
+    }
     // gene lists are padded with -1 up to whole T-tile blocks plus a pair of tiles (the pair kernel copies the ids of
     // two column tiles per step); identity list for "all genes are references" (cached while r is unchanged)
     const int64_t list_cap = rpad + (int64_t)(8 + 8 + 2) * REO_TILE;
@@ -808,6 +817,7 @@ int launch_tables(reo_handle_t h, ReoDev& D, const LevelPlan& P, const uint8_t* 
     p.T = T; p.rank = h->rank; p.world = h->world;
     p.segA0 = P.segA0; p.mixedW = P.mixedW; p.segB0 = P.segB0; p.segB0len = P.segB0len; p.segB1 = P.segB1;
     p.table = D.table.p; p.counter = D.counter.p;
+    p.word_np = S.word_np;
     p.W = S.W; p.WA = P.WA; p.NP = S.NP;
     p.nA = P.nA; p.nB = P.nB; p.padA = P.padA; p.padB = P.padB; p.thrA = P.thrA; p.thrB = P.thrB;
     p.mixed = P.mixed; p.maskA = P.maskA; p.maskB = P.maskB;

@@ -63,7 +63,9 @@ struct __align__(128) P2Aux {
     int8_t rsgn[64];
     int flags, nw, kb, w0;       // first 16 bytes: what every stage needs (kb: index in the stage of the first word
                                  // that is not purely of group A, -1 if none)
-    int I, J, il, jl, rbase, cbase, pad[6];
+    int I, J, il, jl, rbase, cbase;
+    int skip;                    // bit k: word k of the stage has an empty top plane (its chain stops one plane early)
+    int pad[5];
 };
 static_assert(sizeof(P2Aux) == 1024, "P2Aux must stay 1 KB");
 
@@ -226,6 +228,12 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                         A->il = I - B0; A->jl = Ja - J0; A->rbase = B0 * REO_TILE; A->cbase = J0 * REO_TILE;
                         A->flags = tf | (first ? P2F_FIRST_J : 0) | (last ? P2F_LAST_J : 0) |
                                    ((last && last_pair) ? P2F_LAST_ITEM : 0);
+                        {   // words of this stage whose top plane is empty (header fields are published by the arrive below)
+                            int skip = 0;
+                            if (p.word_np)
+                                for (int q = 0; q < nw; ++q) skip |= (int)(p.word_np[word_of(w0 + q)] < NP) << q;
+                            A->skip = skip;
+                        }
                         uint32_t bytes = (uint32_t)nw * op_bytes * (hasB ? 3u : 2u);
                         // gene ids travel with the first stage of a tile pair (orientation of the tie coin) and, together
                         // with the signs, with its last stage (table update): consumers keep none of them in registers
@@ -417,6 +425,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
         // word of this stage that is the first not purely of group A (the class of group A is taken there); the
         // plain words before and after it run in a loop without any test
         const bool has_b = kb >= 0 && kb < nw;
+        const uint32_t skipmask = (uint32_t)A->skip;
         // UNI: one tie-coin orientation for the whole 4 x 8 block (all but the blocks on the diagonal / matrix edges)
         auto words = [&](auto uni_c) {
             constexpr bool UNI = decltype(uni_c)::value;
@@ -425,7 +434,9 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
             const uint32_t cfB = ((obits & 16u) << 3) | ((obits & 32u) << 10) | ((obits & 64u) << 17) | ((obits & 128u) << 24);
             uint4 xn = lds_v4(xa), yn = lds_v4(ya), zn = lds_v4(ya + zoff);
             // borrow chain of one word over all planes; leaves the operands of the next word's plane 0 in xn/yn/zn
-            auto chain = [&](uint32_t (&bor)[4][NB]) {
+            // (npl_c: planes to run through -- NPT, or NPT - 1 for a word whose top plane is empty)
+            auto chain = [&](uint32_t (&bor)[4][NB], auto npl_c) {
+                constexpr int NPL = decltype(npl_c)::value;
                 {
                     const uint32_t x[4] = {xn.x, xn.y, xn.z, xn.w};
                     const uint32_t y[NB] = {yn.x, yn.y, yn.z, yn.w, zn.x, zn.y, zn.z, zn.w};
@@ -457,12 +468,12 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                 }
                 if (NPT > 0) {
 #pragma unroll
-                    for (int pl = 1; pl < (NPT > 0 ? NPT : 1); ++pl) {
+                    for (int pl = 1; pl < (NPL > 0 ? NPL : 1); ++pl) {
                         const uint32_t x[4] = {xn.x, xn.y, xn.z, xn.w};
                         const uint32_t y[NB] = {yn.x, yn.y, yn.z, yn.w, zn.x, zn.y, zn.z, zn.w};
                         // next plane, or plane 0 of the next word (one word = op_bytes further; past the last word of
                         // the stage this reads shared memory that is simply not used)
-                        const uint32_t nx = (pl + 1 < NPT) ? (uint32_t)(pl + 1) * 256u : op_bytes;
+                        const uint32_t nx = (pl + 1 < NPL) ? (uint32_t)(pl + 1) * 256u : op_bytes;
                         xn = lds_v4(xa + nx); yn = lds_v4(ya + nx); zn = lds_v4(ya + zoff + nx);
 #pragma unroll
                         for (int b = 0; b < NB; ++b)
@@ -484,12 +495,16 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                 }
                 xa += op_bytes; ya += op_bytes;
             };
+            constexpr std::integral_constant<int, NPT> full_c{};
             int done = 0;
             for (;;) {
                 const int end = (has_b && done <= kb) ? kb : nw;
                 for (; done < end; ++done) {          // plain words
                     uint32_t bor[4][NB];
-                    chain(bor);
+                    // an all-zero plane leaves the borrow as it is: a word whose samples need one rank bit less than
+                    // the widest sample of the matrix stops one plane early (most words of single-cell data)
+                    if (UNI && NPT > 2 && ((skipmask >> done) & 1u)) chain(bor, std::integral_constant<int, (NPT > 2 ? NPT - 1 : NPT)>{});
+                    else chain(bor, full_c);
                     add_counts(bor, 0u, false);
                 }
                 if (done >= nw) break;
@@ -497,12 +512,12 @@ __global__ void __launch_bounds__(P2_THREADS, P2_CTAS_PER_SM) reo_pair2_kernel(c
                 uint32_t bor[4][NB];
                 if (!p.mixed) {
                     flushA_all();
-                    chain(bor);
+                    chain(bor, full_c);
                     add_counts(bor, 0u, false);
                 } else {
                     // the word shared by the tails of both groups: count group A's slots, classify, then
                     // count group B's slots (the masks select real samples only: no pad slots are counted)
-                    chain(bor);
+                    chain(bor, full_c);
                     add_counts(bor, p.maskA, true);
                     flushA_all();
                     add_counts(bor, p.maskB, true);

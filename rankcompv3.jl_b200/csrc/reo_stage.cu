@@ -640,6 +640,32 @@ unshard_planes_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ pl
         for (int i = threadIdx.x; i < wb4; i += blockDim.x) dst[i] = src[i];
     }
 }
+// ---- planes in use per sample word --------------------------------------------------------------
+// word_np[w] = 1 + the highest rank plane of word w in which any gene has a bit (1 = the coin plane only).  The dense
+// ranks of a sample need only as many bits as it has distinct values, and B is the maximum over ALL samples: the 32
+// samples of most words need fewer planes (single-cell counts: 6 bits for all but a few cells, B = 7), and a borrow-chain
+// step over an all-zero plane is the identity, so the pair kernel skips it.  One CTA per word, top plane first.
+__global__ void __launch_bounds__(256)
+word_planes_kernel(const uint32_t* __restrict__ planes, int NT, int W, int NP, uint8_t* __restrict__ word_np) {
+    const int w = blockIdx.x;
+    int np = 1;
+    for (int p = NP - 1; p >= 1; --p) {
+        uint32_t any = 0u;
+        for (int i = threadIdx.x; i < NT * REO_TILE; i += 256) {
+            const int t = i >> 6, l = i & 63;
+            any |= planes[(((size_t)t * W + w) * NP + p) * REO_TILE + l];
+        }
+        if (__syncthreads_or(any != 0u)) { np = p + 1; break; }
+    }
+    if (threadIdx.x == 0) word_np[w] = (uint8_t)np;
+}
+
+cudaError_t reo_launch_word_planes(const uint32_t* planes, int NT, int W, int NP, uint8_t* word_np, cudaStream_t st) {
+    if (W <= 0) return cudaSuccess;
+    word_planes_kernel<<<W, 256, 0, st>>>(planes, NT, W, NP, word_np);
+    return cudaGetLastError();
+}
+
 cudaError_t reo_launch_unshard_planes(const uint32_t* gathered, uint32_t* planes, int NT, int W, int wq, int wb,
                                       cudaStream_t st) {
     dim3 grid(NT, std::min(W, 65535));
