@@ -415,8 +415,10 @@ def main():
         n_sms = torch.cuda.get_device_properties(local).multi_processor_count
         B = st_dev[-1]["rank_bits"]
         W = st_dev[-1]["sample_words"]
-        # LOP3 lane-ops issued: (B+1) per 32 sample slots of every evaluated pair, padded slots included
-        lop3 = k2_cmp / c * (W * 32) * (B + 1) / 32.0
+        # LOP3 lane-ops issued: one per plane the chain runs per 32 sample slots of every evaluated pair, padded slots
+        # included -- B + 1 planes, less the empty top plane of the words that skip it (reo_stats.planes_per_word)
+        planes = st_dev[-1].get("planes_per_word") or float(B + 1)
+        lop3 = k2_cmp / c * (W * 32) * planes / 32.0
         lop3_peak = n_sms * 64 * sm_mhz * 1e6               # the ALU pipe issues 64 LOP3 lanes per clock per SM
         p_cmp = n_sms * 128 * sm_mhz * 1e6                  # SMs x 128 lane-ops/clk x f_SM
         ach_cmp = k2_cmp / (k2_ms * 1e-3) if k2_ms > 0 else 0.0
@@ -433,7 +435,7 @@ def main():
                 "traffic": tr.get("dram_bytes_per_launch"), "traffic_note": tr.get("note", "no ncu capture committed for this workload"),
                 "launches": k2_launches, "ms_per_launch": k2_ms / max(k2_launches, 1),
                 "kernel_share_of_step": k2_ms / ms_dev if ms_dev > 0 else None,
-                "rank_bits": B, "sample_words": W, "sm_mhz_used": sm_mhz}
+                "rank_bits": B, "sample_words": W, "planes_per_word": planes, "sm_mhz_used": sm_mhz}
         # K1 (rank + bit-plane staging) against the measured HBM copy bandwidth: SURVEY 8d algorithmic bytes =
         # read r*c*8 (Int64 input) + write r*c*(B+1)/8 (bit planes)
         k1_ms = sum(s["ms_stage"] for s in st_dev) / len(st_dev)
@@ -502,7 +504,7 @@ def run_secondary(pkg, torch, h, device, dev_cells, gid_cells):
         t = sum(ms) / len(ms)
         return {"ms_per_job": t, "value": st["compares"] / (t * 1e-3), "unit": UNIT, "evaluations": st["iters_done"],
                 "pairs_ms": st["ms_pairs"], "staging_ms": st["ms_stage"], "stats_ms": st["ms_stats"], "rank_bits": st["rank_bits"],
-                "lop3_pipe_frac": (st["compares"] / mat_c(mat) * st["sample_words"] * (st["rank_bits"] + 1)) / (st["ms_pairs"] * 1e-3)
+                "lop3_pipe_frac": (st["compares"] / mat_c(mat) * st["sample_words"] * (st.get("planes_per_word") or (st["rank_bits"] + 1))) / (st["ms_pairs"] * 1e-3)
                                   / (torch.cuda.get_device_properties(0).multi_processor_count * 64 * 1.965e9)
                 if st["ms_pairs"] > 0 and st["rank_bits"] > 0 else None}
 

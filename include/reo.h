@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define REO_VERSION 200 /* 0.2.0 */
+#define REO_VERSION 201 /* 0.2.0 */
 
 typedef struct reo_handle_s* reo_handle_t;
 
@@ -79,6 +79,9 @@ typedef struct {
     int64_t ordered_triples;            /* (row gene, column gene, sample) triples the evaluated pairs stand
                                            for: rows x columns x samples per table build (W_ord); `compares`
                                            counts each mirrored pair once, as the reference does (src:366-372) */
+    double planes_per_word;             /* bit planes the pair kernel's borrow chain runs per 32-sample word, averaged
+                                           over the staged words (<= rank_bits + 1: a word whose samples need fewer
+                                           rank bits than the widest sample skips its empty top plane)          */
 } reo_stats;
 
 /* Multi-process sharding hook: all-gather `bytes_per_rank` bytes per rank, in place, inside the

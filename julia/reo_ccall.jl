@@ -30,6 +30,7 @@ struct ReoStats
     pair_launches::Int32
     kernel_launches::Int32
     ordered_triples::Int64
+    planes_per_word::Float64
 end
 
 const REO_OUT_PINNED = UInt32(2)

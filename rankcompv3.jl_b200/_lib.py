@@ -49,6 +49,7 @@ class ReoStats(C.Structure):
         ("pair_launches", C.c_int32),
         ("kernel_launches", C.c_int32),
         ("ordered_triples", C.c_int64),
+        ("planes_per_word", C.c_double),
     ]
 
 

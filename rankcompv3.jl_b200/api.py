@@ -249,7 +249,8 @@ class Reo:
                      n_ref=list(st.n_ref[:ne]), rank_bits=int(st.rank_bits), sample_words=int(st.sample_words),
                      compares=int(st.compares), ms_stage=st.ms_stage, ms_pairs=st.ms_pairs, ms_stats=st.ms_stats,
                      ms_total=st.ms_total, ms_wall=st.ms_wall, pair_launches=int(st.pair_launches),
-                     kernel_launches=int(st.kernel_launches), ordered_triples=int(st.ordered_triples))
+                     kernel_launches=int(st.kernel_launches), ordered_triples=int(st.ordered_triples),
+                     planes_per_word=float(st.planes_per_word))
         # [K, r, 15] view of the library's column-major output (no copy)
         return DegResult(result.transpose(0, 2, 1), updown, final_ref, [int(v) for v in iters], stats)
 

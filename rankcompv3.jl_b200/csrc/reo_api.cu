@@ -675,9 +675,14 @@ int do_stage(reo_handle_t h, const void* data, int dtype, int64_t r, int64_t c, 
     static const bool no_skip = getenv("REO_NO_PLANE_SKIP") != nullptr;
     if (!S.flt && !no_skip) {   // which planes each sample word really uses (the pair kernel skips an empty top plane)
         CK(D.word_np.ensure((size_t)W));
-        CKL(reo_launch_word_planes(S.planes, S.NT, W, S.NP, D.word_np.p, D.st));
+        CK(cudaMemsetAsync(D.flags.p + 10, 0, sizeof(int), D.st));
+        CKL(reo_launch_word_planes(S.planes, S.NT, W, S.NP, D.word_np.p, D.flags.p + 10, D.st));
+        CK(cudaMemcpyAsync(D.h_counts + 12, D.flags.p + 10, sizeof(int), cudaMemcpyDeviceToHost, D.st));
         h->kernel_launches++;
         S.word_np = D.word_np.p;
+        S.planes_per_word = -1.0;   // read from h_counts[12] once the stream has been synchronised (stats)
+    } else {
+        S.planes_per_word = (double)S.NP;
     }
     // gene lists are padded with -1 up to whole T-tile blocks plus a pair of tiles (the pair kernel copies the ids of
     // two column tiles per step); identity list for "all genes are references" (cached while r is unchanged)
@@ -1613,6 +1618,7 @@ int reo_identify_degs(reo_handle_t h, const void* data, int dtype, int64_t r, in
     if (stats) {
         st_local.rank_bits = S.B; st_local.sample_words = S.W; st_local.compares = h->compares;
         st_local.ordered_triples = h->ordered_triples;
+        st_local.planes_per_word = S.planes_per_word < 0.0 ? (double)D.h_counts[12] / std::max(1, S.W) : S.planes_per_word;
         st_local.ms_stage = ms_stage; st_local.ms_pairs = ms_pairs; st_local.ms_total = ms_total;
         st_local.ms_stats = ms_total - ms_stage - ms_pairs;
         st_local.pair_launches = h->pair_launches; st_local.kernel_launches = h->kernel_launches;

@@ -46,6 +46,7 @@ struct ReoStaged {
     int NP = 0;        // planes = B + 1
     uint32_t* planes = nullptr;      // [NT][W][NP][64]; float path: [NT][W][REO_FLT_OPWORDS]
     uint8_t* word_np = nullptr;      // [W] planes of each sample word that hold anything (coin plane + rank bits its samples need)
+    double planes_per_word = 0.0;    // mean planes the pair kernel runs per word (NP when nothing is skipped)
     bool flt = false;                // non-integral input: raw FP64 values instead of rank planes
     bool flt_f32 = false;            // ... that came from a Float32 matrix: differences are rounded to Float32 (src:72 in Julia)
     std::vector<int> lev_word0;      // first word of each level
@@ -152,7 +153,7 @@ cudaError_t reo_launch_rank_fallback(const void* data, int dtype, int64_t r, int
 cudaError_t reo_launch_bitplanes(const void* ranks, int rank_bytes, int64_t rpad, int64_t r, const int32_t* sample_of_slot,
                                  int NT, int w_lo, int w_n, int w_stride, int NP, uint32_t seed_lo, uint32_t seed_hi,
                                  uint32_t* planes, cudaStream_t st);
-cudaError_t reo_launch_word_planes(const uint32_t* planes, int NT, int W, int NP, uint8_t* word_np, cudaStream_t st);
+cudaError_t reo_launch_word_planes(const uint32_t* planes, int NT, int W, int NP, uint8_t* word_np, int* run_sum, cudaStream_t st);
 cudaError_t reo_launch_unshard_planes(const uint32_t* gathered, uint32_t* planes, int NT, int W, int wq, int wb,
                                       cudaStream_t st);
 cudaError_t reo_launch_gather_panel(const uint32_t* planes, int W, int NP, const int32_t* col_gene, int ntc,

@@ -646,7 +646,7 @@ unshard_planes_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ pl
 // samples of most words need fewer planes (single-cell counts: 6 bits for all but a few cells, B = 7), and a borrow-chain
 // step over an all-zero plane is the identity, so the pair kernel skips it.  One CTA per word, top plane first.
 __global__ void __launch_bounds__(256)
-word_planes_kernel(const uint32_t* __restrict__ planes, int NT, int W, int NP, uint8_t* __restrict__ word_np) {
+word_planes_kernel(const uint32_t* __restrict__ planes, int NT, int W, int NP, uint8_t* __restrict__ word_np, int* __restrict__ run_sum) {
     const int w = blockIdx.x;
     int np = 1;
     for (int p = NP - 1; p >= 1; --p) {
@@ -657,12 +657,15 @@ word_planes_kernel(const uint32_t* __restrict__ planes, int NT, int W, int NP, u
         }
         if (__syncthreads_or(any != 0u)) { np = p + 1; break; }
     }
-    if (threadIdx.x == 0) word_np[w] = (uint8_t)np;
+    if (threadIdx.x == 0) {
+        word_np[w] = (uint8_t)np;
+        atomicAdd(run_sum, (np < NP && NP > 2) ? NP - 1 : NP);   // planes the pair kernel will run for this word
+    }
 }
 
-cudaError_t reo_launch_word_planes(const uint32_t* planes, int NT, int W, int NP, uint8_t* word_np, cudaStream_t st) {
+cudaError_t reo_launch_word_planes(const uint32_t* planes, int NT, int W, int NP, uint8_t* word_np, int* run_sum, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
-    word_planes_kernel<<<W, 256, 0, st>>>(planes, NT, W, NP, word_np);
+    word_planes_kernel<<<W, 256, 0, st>>>(planes, NT, W, NP, word_np, run_sum);
     return cudaGetLastError();
 }
 

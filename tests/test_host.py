@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert declared == set(pkg._lib.SYMBOLS), declared ^ set(pkg._lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.reo_version() == 200
+    assert lib.reo_version() == 201
 
 
 def test_no_gpu_fails_loudly(pkg):
