@@ -242,6 +242,30 @@ def test_identify_degs_matches_oracle(reo, oracle, coracle, seed, r, n1, n2, n3,
     check_full(out2, want2)
 
 
+def test_words_with_an_empty_top_plane_skip_it(reo, oracle, coracle):
+    """One sample with 300 distinct values sets B = 9 for the whole matrix; every other sample has a handful, so all words
+    but the first have empty top planes and the pair kernel stops their borrow chains one plane early
+    (reo_stats.planes_per_word < B + 1).  Results must not change: the oracle knows nothing about planes."""
+    rng = np.random.default_rng(123)
+    r, n1, n2 = 300, 70, 60
+    mu = np.exp(rng.normal(0.3, 0.8, r))
+    data = rng.poisson(mu[:, None] * np.ones((1, n1 + n2))).astype(np.int64)
+    data[:25, n1:] += 2
+    data[:, 5] = rng.permutation(r)                       # the one wide sample (first word of the first group)
+    gid = np.array([0] * n1 + [1] * n2, dtype=np.int32)
+    ref = np.arange(r) % 3 != 0
+    thr = coracle.thresholds_for(gid, 2, 0.01)
+    want = coracle.identify_degs(data, gid, 2, thr, 1.0, 0.05, ref, 128, 5, seed=7)
+    out = reo.identify_degs(data, gid, 2, ref, 0.01, 1.0, 0.05, 128, 5)
+    check_full(out, want)
+    assert out.stats["rank_bits"] == 9
+    assert out.stats["sample_words"] == 5
+    assert abs(out.stats["planes_per_word"] - (10 + 4 * 9) / 5) < 1e-9
+    # all-genes build (symmetric sweep) on the same staged planes
+    tab, _ = coracle.block_tables(data, gid, 2, thr, np.arange(r), seed=7)
+    assert np.array_equal(reo.tables(0, np.ones(r, bool), thresholds=thr), tab)
+
+
 def test_identify_degs_reference_signature(reo, pkg, oracle, coracle):
     """The reference-named wrapper returns the r x (1+16K) matrix of src:430/437."""
     data, group = small_case(5, 120, 8, 8)
