@@ -78,7 +78,10 @@ def test_pair_plan_covers_every_tile_pair_once(pkg):
     (row tile, column tile) is evaluated exactly once, in every shape, at any rank count."""
     from importlib import import_module
     dist = import_module(pkg.__name__ + ".dist")
-    for r, ncols, W, NP in ((30000, 30000, 625, 8), (20000, 3000, 7, 13), (20000, 15000, 7, 13), (700, 700, 1, 10), (130, 70, 3, 5)):
+    shapes = ((30000, 30000, 625, 8), (20000, 3000, 7, 13), (20000, 15000, 7, 13), (700, 700, 1, 10), (130, 70, 3, 5),
+              # few reference columns against all genes (signed updates): supertiles narrower than they are tall
+              (30000, 64, 625, 8), (30000, 128, 625, 8), (30000, 448, 625, 8), (20000, 500, 7, 13), (5000, 200, 40, 9))
+    for r, ncols, W, NP in shapes:
         for world in (1, 3, 8):
             seen = {}
             sizes = []
